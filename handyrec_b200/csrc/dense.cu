@@ -1,0 +1,347 @@
+// dense.cu -- Dense layers of the reference DNN (layers/core.py:53-78; Keras Dense = x@W+b),
+// forward and both backward GEMMs, fp32 FFMA path.
+//
+// One tiled SGEMM template serves the three products (row-major everywhere):
+//   fwd    y [M,N] = act( x[M,K]  @ w[K,N] + bias )        A = x   (k contiguous), B = w  (n contiguous)
+//   bwd_x  dx[M,K] = (dz[M,N] @ w[K,N]^T) * act'(a_prev)   A = dz  (k contiguous), B = w^T (k contiguous)
+//   bwd_w  dw[K,N] =  x[M,K]^T @ dz[M,N]                   A = x^T (m contiguous), B = dz (n contiguous), split over M
+// 128x128x16 CTA tile, 256 threads, 8x8 register tile, register-prefetch double buffering.
+// Bound: fp32 FFMA pipe (148 SMs x 128 FMA/clk).  The tcgen05 3xTF32 path lives in gemm_tc.cu.
+#include "common.cuh"
+
+namespace hrb {
+
+constexpr int BM = 128, BN = 128, BK = 16, TM = 8, TN = 8;
+constexpr int PAD = 4;
+
+enum Epilogue { EPI_BIAS_ACT = 0, EPI_ACT_GRAD = 1, EPI_PLAIN = 2 };
+
+struct GemmArgs {
+  const float* A;
+  const float* B;
+  float* C;
+  int64_t lda, ldb, ldc;
+  int64_t M;     // rows of C
+  int32_t N;     // cols of C
+  int64_t Kred;  // reduction length
+  // epilogue
+  const float* bias;   // [N]           (EPI_BIAS_ACT)
+  const float* aprev;  // [M, ldaprev]  (EPI_ACT_GRAD)
+  int64_t ldaprev;
+  int32_t act;
+  // split over the reduction dim (bwd_w): slice z handles [z*kslice, min(Kred,(z+1)*kslice)) and writes C + z*M*ldc
+  int64_t kslice;
+};
+
+// load a 4-vector with per-element bounds masking along the contiguous dim
+__device__ __forceinline__ float4 load4(const float* __restrict__ p, int64_t idx_contig, int64_t extent, bool row_ok,
+                                        bool vec) {
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (!row_ok || idx_contig >= extent) return v;
+  if (vec && idx_contig + 3 < extent) return __ldg(reinterpret_cast<const float4*>(p));
+  v.x = __ldg(p);
+  if (idx_contig + 1 < extent) v.y = __ldg(p + 1);
+  if (idx_contig + 2 < extent) v.z = __ldg(p + 2);
+  if (idx_contig + 3 < extent) v.w = __ldg(p + 3);
+  return v;
+}
+
+// TA: A is stored [k][m] (m contiguous);  !TA: A is stored [m][k] (k contiguous)
+// TB: B is stored [n][k] (k contiguous);  !TB: B is stored [k][n] (n contiguous)
+template <bool TA, bool TB, int EPI>
+__global__ void __launch_bounds__(256) sgemm_kernel(GemmArgs g, bool vecA, bool vecB, bool vecC) {
+  __shared__ __align__(16) float As[2][BK][BM + PAD];
+  __shared__ __align__(16) float Bs[2][BK][BN + PAD];
+  const int tid = threadIdx.x;
+  const int64_t m0 = (int64_t)blockIdx.y * BM;
+  const int n0 = blockIdx.x * BN;
+  const int64_t kbeg = (int64_t)blockIdx.z * g.kslice;
+  const int64_t kend = min(g.Kred, kbeg + g.kslice);
+  float* __restrict__ C = g.C + (int64_t)blockIdx.z * g.M * g.ldc;
+
+  const int ty = tid / 16, tx = tid % 16;  // 16x16 threads, each 8x8 outputs (rows ty*8.., cols tx*8..)
+  float acc[TM][TN];
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+  float4 ra[2], rb[2];
+  auto gload = [&](int64_t k0) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      if (!TA) {  // 128 rows x 16 k: thread -> (m = tid/4 + 64 i, k4 = (tid%4)*4)
+        const int m = tid / 4 + 64 * i, k4 = (tid % 4) * 4;
+        const int64_t gm = m0 + m, gk = k0 + k4;
+        ra[i] = load4(g.A + gm * g.lda + gk, gk, kend, gm < g.M, vecA);
+      } else {    // 16 k x 128 m: thread -> (k = tid/32 + 8 i, m4 = (tid%32)*4)
+        const int k = tid / 32 + 8 * i, m4 = (tid % 32) * 4;
+        const int64_t gm = m0 + m4, gk = k0 + k;
+        ra[i] = load4(g.A + gk * g.lda + gm, gm, g.M, gk < kend, vecA);
+      }
+      if (!TB) {  // 16 k x 128 n
+        const int k = tid / 32 + 8 * i, n4 = (tid % 32) * 4;
+        const int64_t gn = n0 + n4, gk = k0 + k;
+        rb[i] = load4(g.B + gk * g.ldb + gn, gn, g.N, gk < kend, vecB);
+      } else {    // 128 n x 16 k
+        const int n = tid / 4 + 64 * i, k4 = (tid % 4) * 4;
+        const int64_t gn = n0 + n, gk = k0 + k4;
+        rb[i] = load4(g.B + gn * g.ldb + gk, gk, kend, gn < g.N, vecB);
+      }
+    }
+  };
+  auto sstore = [&](int buf) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      if (!TA) {
+        const int m = tid / 4 + 64 * i, k4 = (tid % 4) * 4;
+        As[buf][k4 + 0][m] = ra[i].x; As[buf][k4 + 1][m] = ra[i].y;
+        As[buf][k4 + 2][m] = ra[i].z; As[buf][k4 + 3][m] = ra[i].w;
+      } else {
+        const int k = tid / 32 + 8 * i, m4 = (tid % 32) * 4;
+        *reinterpret_cast<float4*>(&As[buf][k][m4]) = ra[i];
+      }
+      if (!TB) {
+        const int k = tid / 32 + 8 * i, n4 = (tid % 32) * 4;
+        *reinterpret_cast<float4*>(&Bs[buf][k][n4]) = rb[i];
+      } else {
+        const int n = tid / 4 + 64 * i, k4 = (tid % 4) * 4;
+        Bs[buf][k4 + 0][n] = rb[i].x; Bs[buf][k4 + 1][n] = rb[i].y;
+        Bs[buf][k4 + 2][n] = rb[i].z; Bs[buf][k4 + 3][n] = rb[i].w;
+      }
+    }
+  };
+
+  int buf = 0;
+  if (kbeg < kend) {
+    gload(kbeg);
+    sstore(0);
+  }
+  __syncthreads();
+  for (int64_t k0 = kbeg; k0 < kend; k0 += BK) {
+    const bool more = k0 + BK < kend;
+    if (more) gload(k0 + BK);
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      // split 8 = 4 + 4 with a 64-column stride between halves keeps LDS.128 conflict-free
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][kk][ty * 4]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][kk][ty * 4 + 64]);
+      const float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][kk][tx * 4]);
+      const float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][kk][tx * 4 + 64]);
+      const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    if (more) {
+      sstore(buf ^ 1);
+      __syncthreads();
+      buf ^= 1;
+    }
+  }
+
+  // epilogue: rows {ty*4..+3, 64+ty*4..+3}, cols {tx*4..+3, 64+tx*4..+3}
+#pragma unroll
+  for (int i = 0; i < TM; ++i) {
+    const int64_t gm = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+    if (gm >= g.M) continue;
+#pragma unroll
+    for (int jh = 0; jh < 2; ++jh) {
+      const int gn = n0 + jh * 64 + tx * 4;
+      if (gn >= g.N) continue;
+      float v[4] = {acc[i][jh * 4 + 0], acc[i][jh * 4 + 1], acc[i][jh * 4 + 2], acc[i][jh * 4 + 3]};
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        if (gn + c < g.N) {
+          if (EPI == EPI_BIAS_ACT) {
+            const float bz = g.bias != nullptr ? __ldg(g.bias + gn + c) : 0.f;
+            v[c] = act_apply(g.act, v[c] + bz);
+          } else if (EPI == EPI_ACT_GRAD) {
+            if (g.aprev != nullptr) v[c] *= act_grad_from_out(g.act, __ldg(g.aprev + gm * g.ldaprev + gn + c));
+          }
+        }
+      }
+      float* cp = C + gm * g.ldc + gn;
+      if (vecC && gn + 3 < g.N) {
+        *reinterpret_cast<float4*>(cp) = make_float4(v[0], v[1], v[2], v[3]);
+      } else {
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          if (gn + c < g.N) cp[c] = v[c];
+      }
+    }
+  }
+}
+
+// fixed-order reduction of the split partials: out[i] = sum_z part[z, i]
+__global__ void __launch_bounds__(256) split_reduce_kernel(const float* __restrict__ part, int64_t rows, int32_t cols,
+                                                          int64_t ld_part, int32_t splits, float* __restrict__ out,
+                                                          int64_t ld_out) {
+  const int64_t total = rows * cols;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / cols;
+    const int c = (int)(i - r * cols);
+    float s = 0.f;
+    for (int z = 0; z < splits; ++z) s += part[((int64_t)z * rows + r) * ld_part + c];
+    out[r * ld_out + c] = s;
+  }
+}
+
+// column sums of dz[M,N] (bias gradient), two fixed-order passes: per-CTA partials then a final sum
+__global__ void __launch_bounds__(256) colsum_partial_kernel(const float* __restrict__ dz, int64_t lddz, int64_t M,
+                                                            int32_t N, int64_t rows_per_block,
+                                                            float* __restrict__ part /* [gridDim.y, N] */) {
+  const int n = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int ry = threadIdx.x >> 5;  // 8 row lanes
+  __shared__ float red[8][33];
+  const int64_t r0 = (int64_t)blockIdx.y * rows_per_block;
+  const int64_t r1 = min(M, r0 + rows_per_block);
+  float s = 0.f;
+  if (n < N)
+    for (int64_t r = r0 + ry; r < r1; r += 8) s += __ldg(dz + r * lddz + n);
+  red[ry][threadIdx.x & 31] = s;
+  __syncthreads();
+  if (ry == 0 && n < N) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += red[k][threadIdx.x & 31];
+    part[(int64_t)blockIdx.y * N + n] = t;
+  }
+}
+
+__global__ void __launch_bounds__(256) act_bwd_kernel(const float* __restrict__ y, const float* __restrict__ dy, int64_t n,
+                                                     int32_t act, float* __restrict__ dz) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    dz[i] = dy[i] * act_grad_from_out(act, y[i]);
+}
+
+static inline bool vec_ok(const void* p, int64_t ld) { return aligned16(p) && ld % 4 == 0; }
+
+static int pick_splits(int64_t M, int32_t K, int32_t N) {
+  const int tiles = ((K + BM - 1) / BM) * ((N + BN - 1) / BN);
+  int splits = (2 * sm_count() + tiles - 1) / tiles;
+  const int64_t max_by_len = (M + 4 * BK - 1) / (4 * BK);
+  if (splits > max_by_len) splits = (int)max_by_len;
+  if (splits < 1) splits = 1;
+  if (splits > 256) splits = 256;
+  return splits;
+}
+
+}  // namespace hrb
+
+using namespace hrb;
+
+template <bool TA, bool TB, int EPI>
+static int launch_sgemm(const GemmArgs& g, int splits, cudaStream_t st) {
+  dim3 grid((g.N + BN - 1) / BN, (unsigned)((g.M + BM - 1) / BM), splits);
+  sgemm_kernel<TA, TB, EPI><<<grid, 256, 0, st>>>(g, vec_ok(g.A, g.lda), vec_ok(g.B, g.ldb), vec_ok(g.C, g.ldc));
+  HRB_LAUNCH_CHECK();
+  return HRB_OK;
+}
+
+// implemented in gemm_tc.cu (tcgen05 3xTF32); return HRB_UNSUPPORTED when the shape is not covered
+int hrb_tc_dense_fwd(const float* x, int64_t ldx, const float* w, int64_t ldw, const float* bias, int64_t M, int32_t K,
+                     int32_t N, int32_t act, float* y, int64_t ldy, cudaStream_t st);
+int hrb_tc_dense_bwd_x(const float* dz, int64_t lddz, const float* w, int64_t ldw, int64_t M, int32_t K, int32_t N,
+                       const float* a_prev, int64_t lda_prev, int32_t act_prev, float* dx, int64_t lddx, cudaStream_t st);
+int hrb_tc_dense_bwd_w(const float* x, int64_t ldx, const float* dz, int64_t lddz, int64_t M, int32_t K, int32_t N,
+                       float* dw, int64_t lddw, void* workspace, size_t workspace_bytes, cudaStream_t st);
+
+HRB_API int hrb_dense_fwd(const float* x, int64_t ldx, const float* w, int64_t ldw, const float* bias, int64_t M,
+                          int32_t K, int32_t N, int32_t act, float* y, int64_t ldy, int32_t mode, void* stream) {
+  HRB_REQUIRE(x && w && y && M >= 0 && K > 0 && N > 0 && ldx >= K && ldw >= N && ldy >= N, "hrb_dense_fwd: bad argument");
+  HRB_REQUIRE(act >= HRB_ACT_LINEAR && act <= HRB_ACT_TANH, "hrb_dense_fwd: unknown activation %d", act);
+  if (M == 0) return HRB_OK;
+  if (mode != HRB_GEMM_FP32) {
+    int rc = hrb_tc_dense_fwd(x, ldx, w, ldw, bias, M, K, N, act, y, ldy, (cudaStream_t)stream);
+    if (rc == HRB_OK) return rc;
+    if (mode == HRB_GEMM_3XTF32 || rc != HRB_UNSUPPORTED) return rc;
+  }
+  GemmArgs g{x, w, y, ldx, ldw, ldy, M, N, K, bias, nullptr, 0, act, K};
+  return launch_sgemm<false, false, EPI_BIAS_ACT>(g, 1, (cudaStream_t)stream);
+}
+
+HRB_API int hrb_dense_bwd_x(const float* dz, int64_t lddz, const float* w, int64_t ldw, int64_t M, int32_t K, int32_t N,
+                            const float* a_prev, int64_t lda_prev, int32_t act_prev, float* dx, int64_t lddx,
+                            int32_t mode, void* stream) {
+  HRB_REQUIRE(dz && w && dx && M >= 0 && K > 0 && N > 0 && lddz >= N && ldw >= N && lddx >= K, "hrb_dense_bwd_x: bad argument");
+  HRB_REQUIRE(a_prev == nullptr || lda_prev >= K, "hrb_dense_bwd_x: lda_prev < K");
+  if (M == 0) return HRB_OK;
+  if (mode != HRB_GEMM_FP32) {
+    int rc = hrb_tc_dense_bwd_x(dz, lddz, w, ldw, M, K, N, a_prev, lda_prev, act_prev, dx, lddx, (cudaStream_t)stream);
+    if (rc == HRB_OK) return rc;
+    if (mode == HRB_GEMM_3XTF32 || rc != HRB_UNSUPPORTED) return rc;
+  }
+  // dx[M,K] = dz[M,N] @ w[K,N]^T : C cols = K, reduction = N, B = w stored [K][N] = "[n][k]" with roles swapped
+  GemmArgs g{dz, w, dx, lddz, ldw, lddx, M, K, N, nullptr, a_prev, lda_prev, act_prev, N};
+  return launch_sgemm<false, true, EPI_ACT_GRAD>(g, 1, (cudaStream_t)stream);
+}
+
+HRB_API int hrb_dense_bwd_w_workspace(int64_t M, int32_t K, int32_t N, size_t* bytes) {
+  HRB_REQUIRE(bytes && M >= 0 && K > 0 && N > 0, "hrb_dense_bwd_w_workspace: bad argument");
+  const int splits = pick_splits(M, K, N);
+  const size_t part = (size_t)splits * K * (size_t)((N + 3) / 4 * 4) * sizeof(float);
+  const size_t colsum = (size_t)256 * N * sizeof(float);
+  *bytes = part + colsum + 512;
+  return HRB_OK;
+}
+
+HRB_API int hrb_dense_bwd_w(const float* x, int64_t ldx, const float* dz, int64_t lddz, int64_t M, int32_t K, int32_t N,
+                            float* dw, int64_t lddw, float* dbias, void* workspace, size_t workspace_bytes, int32_t mode,
+                            void* stream) {
+  HRB_REQUIRE(x && dz && dw && workspace && M >= 0 && K > 0 && N > 0 && ldx >= K && lddz >= N && lddw >= N,
+              "hrb_dense_bwd_w: bad argument");
+  size_t need = 0;
+  hrb_dense_bwd_w_workspace(M, K, N, &need);
+  if (workspace_bytes < need) return fail(HRB_WORKSPACE, "hrb_dense_bwd_w: workspace %zu < required %zu bytes", workspace_bytes, need);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (M == 0) {
+    HRB_CUDA(cudaMemset2DAsync(dw, lddw * sizeof(float), 0, N * sizeof(float), K, st));
+    if (dbias) HRB_CUDA(cudaMemsetAsync(dbias, 0, N * sizeof(float), st));
+    return HRB_OK;
+  }
+  const int splits = pick_splits(M, K, N);
+  const int64_t ldp = (N + 3) / 4 * 4;
+  float* part = (float*)workspace;
+  float* colpart = part + (size_t)splits * K * ldp;
+  bool done = false;
+  if (mode != HRB_GEMM_FP32) {
+    int rc = hrb_tc_dense_bwd_w(x, ldx, dz, lddz, M, K, N, dw, lddw, workspace, workspace_bytes, st);
+    if (rc == HRB_OK) done = true;
+    else if (mode == HRB_GEMM_3XTF32 || rc != HRB_UNSUPPORTED) return rc;
+  }
+  if (!done) {
+    // C[K,N] = x^T @ dz : A = x stored [m][k] -> as A^T it is "[k_red][m_out]" = TA layout with lda = ldx
+    int64_t kslice = (M + splits - 1) / splits;
+    kslice = (kslice + BK - 1) / BK * BK;
+    const int eff_splits = (int)((M + kslice - 1) / kslice);
+    GemmArgs g{x, dz, part, ldx, lddz, ldp, K, N, M, nullptr, nullptr, 0, 0, kslice};
+    int rc = launch_sgemm<true, false, EPI_PLAIN>(g, eff_splits, st);
+    if (rc != HRB_OK) return rc;
+    split_reduce_kernel<<<(unsigned)min((int64_t)sm_count() * 4, ((int64_t)K * N + 255) / 256), 256, 0, st>>>(
+        part, K, N, ldp, eff_splits, dw, lddw);
+    HRB_LAUNCH_CHECK();
+  }
+  if (dbias != nullptr) {
+    int yb = (int)min((int64_t)256, (M + 255) / 256);
+    if (yb < 1) yb = 1;
+    const int64_t rpb = (M + yb - 1) / yb;
+    dim3 grid((N + 31) / 32, yb);
+    colsum_partial_kernel<<<grid, 256, 0, st>>>(dz, lddz, M, N, rpb, colpart);
+    HRB_LAUNCH_CHECK();
+    split_reduce_kernel<<<(N + 255) / 256, 256, 0, st>>>(colpart, 1, N, N, yb, dbias, N);
+    HRB_LAUNCH_CHECK();
+  }
+  return HRB_OK;
+}
+
+HRB_API int hrb_act_bwd(const float* y, const float* dy, int64_t n, int32_t act, float* dz, void* stream) {
+  HRB_REQUIRE(y && dy && dz && n >= 0, "hrb_act_bwd: bad argument");
+  if (n == 0) return HRB_OK;
+  const int64_t blocks = min((int64_t)sm_count() * 8, (n + 255) / 256);
+  act_bwd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(y, dy, n, act, dz);
+  HRB_LAUNCH_CHECK();
+  return HRB_OK;
+}

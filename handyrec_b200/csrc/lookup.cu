@@ -1,0 +1,1115 @@
+// lookup.cu -- embedding gather + mask + masked sequence pooling (forward), fused FM epilogue,
+// and the embedding backward as sort -> segment-reduce -> per-unique-row update (no atomics).
+//
+// Reference arithmetic replaced (paths under /root/reference/handyrec/):
+//   layers/tools.py:87-101      CustomEmbedding (gather, tiled != 0 mask)
+//   layers/sequence.py:26-46    SequencePoolingLayer (masked mean / sum / max)
+//   features/group.py:299-336   FeatureGroup.embedding_lookup (per-feature orchestration)
+//   layers/interaction.py:26-39 FM (fused epilogue of the lookup for DeepFM)
+//   TF autodiff of the above    IndexedSlices scatter-add (+ 2*l2*W), SURVEY a13
+//
+// Data layout in HBM: tables are row-major (rows, D) fp32, rows 16-byte aligned (D % 4 == 0);
+// ids of a batch are one packed int32 matrix ids[B, ids_ld]; the pooled output of a whole group is
+// ONE row-major matrix out[B, out_ld] whose column blocks are the features in reference order, so
+// the DNN input (B, sum D) and the FM input (B, F, D) are the same bytes (layers/utils.py:40-96).
+#include <cub/device/device_radix_sort.cuh>
+#include <new>
+#include <vector>
+
+#include "common.cuh"
+
+namespace hrb {
+
+struct FieldDev {
+  const float* table;
+  int64_t rows;
+  uint32_t key_base;  // first key of this field's table in the global (table,row) key space
+  int32_t dim;
+  int32_t seq_len;
+  int32_t pool;
+  int32_t ids_col;
+  int32_t out_col;
+  int32_t pos_col;  // first column in the dense position space (prefix sum of seq_len)
+  int32_t table_idx;
+};
+
+struct TableDev {
+  float* w;
+  float* m;
+  float* v;
+  int64_t rows;
+  uint32_t key_base;
+  int32_t dim;
+};
+
+}  // namespace hrb
+
+struct hrb_plan {
+  int32_t n_tables = 0, n_fields = 0;
+  std::vector<hrb_table_desc> tables;
+  std::vector<hrb_field_desc> fields;
+  std::vector<hrb::FieldDev> fdev_host;
+  std::vector<hrb::TableDev> tdev_host;
+  uint64_t total_rows = 0;
+  int key_bits = 1;
+  int32_t pos_cols = 0;    // sum of seq_len
+  int32_t out_chunks = 0;  // sum of dim/4
+  int32_t max_dim = 0;
+  bool uniform_dim = true;
+  bool contiguous_out = true;  // out_col_f == out_col_0 + f*D (needs uniform_dim)
+  bool all_len1 = true;
+  bool has_max = false;
+  // device copies (one allocation)
+  void* dev_blob = nullptr;
+  hrb::FieldDev* d_fields = nullptr;
+  hrb::TableDev* d_tables = nullptr;
+  int32_t* d_chunk_field = nullptr;  // out chunk -> field
+  int32_t* d_chunk_q = nullptr;      // out chunk -> 4-column group inside the field
+  int32_t* d_pos_field = nullptr;    // position column -> field
+};
+
+namespace hrb {
+
+constexpr uint32_t kNotMine = 0xFFFFFFFFu;
+
+// ---------------------------------------------------------------------------------------------
+// a5: plain gather + tiled mask (layer face)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) embedding_fwd_kernel(const float* __restrict__ table, int64_t vocab,
+                                                            int32_t chunks /* dim/4 */,
+                                                            const int32_t* __restrict__ ids, int64_t n_ids,
+                                                            float* __restrict__ out, uint8_t* __restrict__ mask,
+                                                            int32_t* __restrict__ oob) {
+  const int64_t total = n_ids * chunks;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  constexpr int U = 4;
+  for (int64_t base = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; base < total; base += stride * U) {
+    int32_t id[U];
+    int64_t item[U];
+    float4 v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      item[u] = base + u * stride;
+      id[u] = item[u] < total ? __ldg(ids + item[u] / chunks) : 0;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (item[u] < total) {
+        const int q = (int)(item[u] % chunks);
+        if (id[u] >= 0 && id[u] < vocab) {
+          v[u] = ldg_nc_na(reinterpret_cast<const float4*>(table + (int64_t)id[u] * chunks * 4) + q);
+        } else if (oob != nullptr) {
+          oob[0] = 1;
+          oob[1] = (int32_t)(item[u] / chunks);
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (item[u] < total) {
+        stg_na(reinterpret_cast<float4*>(out) + item[u], v[u]);
+        if (mask != nullptr) {
+          const uint32_t m = id[u] != 0 ? 0x01010101u : 0u;
+          reinterpret_cast<uint32_t*>(mask)[item[u]] = m;
+        }
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// a6: pooling on a materialised (B,L,D) tensor + (B,L,D) mask (layer face)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) seq_pool_fwd_kernel(const float* __restrict__ x,
+                                                           const uint8_t* __restrict__ mask, int64_t batch,
+                                                           int32_t L, int32_t D, int32_t method,
+                                                           float* __restrict__ out) {
+  const int64_t total = batch * D;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = i / D;
+    const int d = (int)(i - b * D);
+    const float* xp = x + b * (int64_t)L * D + d;
+    const uint8_t* mp = mask + b * (int64_t)L * D + d;
+    if (method == HRB_POOL_MAX) {
+      float best = -INFINITY;
+      for (int l = 0; l < L; ++l) {
+        const float m = mp[(int64_t)l * D] ? 1.0f : 0.0f;
+        best = fmaxf(best, __fsub_rn(xp[(int64_t)l * D], __fmul_rn(1.0f - m, 1e9f)));  // sequence.py:35
+      }
+      out[i] = best;
+    } else {
+      float cnt = 0.f;
+      for (int l = 0; l < L; ++l) cnt += mp[(int64_t)l * D] ? 1.0f : 0.0f;
+      // mean: mask / mask_sum with divide_no_nan (sequence.py:43-44); sum: weight 1
+      const float w = method == HRB_POOL_MEAN ? (cnt > 0.f ? __fdiv_rn(1.0f, cnt) : 0.0f) : 1.0f;
+      float acc = 0.f;
+      for (int l = 0; l < L; ++l)
+        if (mp[(int64_t)l * D]) acc = __fadd_rn(acc, __fmul_rn(xp[(int64_t)l * D], w));
+      out[i] = acc;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) seq_pool_bwd_kernel(const float* __restrict__ x,
+                                                           const uint8_t* __restrict__ mask,
+                                                           const float* __restrict__ dout, int64_t batch,
+                                                           int32_t L, int32_t D, int32_t method,
+                                                           float* __restrict__ dx) {
+  const int64_t total = batch * D;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = i / D;
+    const int d = (int)(i - b * D);
+    const int64_t off = b * (int64_t)L * D + d;
+    const float g = dout[i];
+    if (method == HRB_POOL_MAX) {
+      float best = -INFINITY;
+      for (int l = 0; l < L; ++l) {
+        const float m = mask[off + (int64_t)l * D] ? 1.0f : 0.0f;
+        best = fmaxf(best, __fsub_rn(x[off + (int64_t)l * D], __fmul_rn(1.0f - m, 1e9f)));
+      }
+      int ties = 0;
+      for (int l = 0; l < L; ++l) {
+        const float m = mask[off + (int64_t)l * D] ? 1.0f : 0.0f;
+        ties += (__fsub_rn(x[off + (int64_t)l * D], __fmul_rn(1.0f - m, 1e9f)) == best);
+      }
+      const float share = g / (float)ties;  // TF reduce_max gradient: equal split among ties
+      for (int l = 0; l < L; ++l) {
+        const float m = mask[off + (int64_t)l * D] ? 1.0f : 0.0f;
+        const bool hit = __fsub_rn(x[off + (int64_t)l * D], __fmul_rn(1.0f - m, 1e9f)) == best;
+        dx[off + (int64_t)l * D] = hit ? share : 0.0f;
+      }
+    } else {
+      float cnt = 0.f;
+      for (int l = 0; l < L; ++l) cnt += mask[off + (int64_t)l * D] ? 1.0f : 0.0f;
+      const float w = method == HRB_POOL_MEAN ? (cnt > 0.f ? __fdiv_rn(1.0f, cnt) : 0.0f) : 1.0f;
+      for (int l = 0; l < L; ++l) dx[off + (int64_t)l * D] = mask[off + (int64_t)l * D] ? g * w : 0.0f;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// pooled vector of one (sample, field, 4-column group): the shared inner loop of every fused kernel
+//   PARTIAL: ids are LOCAL rows of a shard, kNotMine marks "owned elsewhere / padding"; returns
+//   the raw sum (or partial max) and the valid count instead of finalising.
+// ---------------------------------------------------------------------------------------------
+template <bool PARTIAL>
+__device__ __forceinline__ float4 pooled_chunk(const FieldDev& f, const int32_t* __restrict__ ids_row, int q,
+                                               float& n_valid, int32_t* __restrict__ oob, int64_t b) {
+  const float4* __restrict__ tab = reinterpret_cast<const float4*>(f.table);
+  const int64_t row_f4 = f.dim >> 2;
+  const int L = f.seq_len;
+  const int32_t* idp = ids_row + f.ids_col;
+  float4 acc;
+  if (f.pool == HRB_POOL_MAX)
+    acc = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+  else
+    acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  float cnt = 0.f;
+  constexpr int U = 8;
+  for (int l0 = 0; l0 < L; l0 += U) {
+    int32_t id[U];
+    bool ok[U];
+    float4 v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) id[u] = (l0 + u < L) ? __ldg(idp + l0 + u) : (PARTIAL ? (int32_t)kNotMine : 0);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      bool valid;
+      if (PARTIAL)
+        valid = (uint32_t)id[u] != kNotMine;
+      else
+        valid = (l0 + u < L) && (f.pool == HRB_POOL_NONE || id[u] != 0);
+      const bool in_range = id[u] >= 0 && (int64_t)id[u] < f.rows;
+      ok[u] = valid;
+      v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (valid) {
+        if (in_range) {
+          v[u] = ldg_nc_na(tab + (int64_t)id[u] * row_f4 + q);
+        } else if (oob != nullptr) {
+          oob[0] = 1;
+          oob[1] = (int32_t)b;
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (ok[u]) {
+        cnt += 1.0f;
+        if (f.pool == HRB_POOL_MAX) {
+          acc.x = fmaxf(acc.x, v[u].x);
+          acc.y = fmaxf(acc.y, v[u].y);
+          acc.z = fmaxf(acc.z, v[u].z);
+          acc.w = fmaxf(acc.w, v[u].w);
+        } else {
+          acc.x += v[u].x;
+          acc.y += v[u].y;
+          acc.z += v[u].z;
+          acc.w += v[u].w;
+        }
+      }
+    }
+  }
+  n_valid = cnt;
+  if (PARTIAL) return acc;
+  if (f.pool == HRB_POOL_MEAN) {
+    // reference: sum_l x * (mask / mask_sum), divide_no_nan -> 0 for an all-padding row (sequence.py:43-46)
+    const float w = cnt > 0.f ? __fdiv_rn(1.0f, cnt) : 0.0f;
+    acc.x *= w;
+    acc.y *= w;
+    acc.z *= w;
+    acc.w *= w;
+  } else if (f.pool == HRB_POOL_MAX) {
+    if (cnt < (float)L) {
+      // padded positions contribute x0 - 1e9 where x0 = row 0 of the table (sequence.py:35-36):
+      // an all-padding row therefore yields fl(W[0,d] - 1e9) (~ -1e9), not 0.
+      const float4 z = ldg_nc_na(tab + q);
+      acc.x = fmaxf(acc.x, __fsub_rn(z.x, 1e9f));
+      acc.y = fmaxf(acc.y, __fsub_rn(z.y, 1e9f));
+      acc.z = fmaxf(acc.z, __fsub_rn(z.z, 1e9f));
+      acc.w = fmaxf(acc.w, __fsub_rn(z.w, 1e9f));
+    }
+  }
+  return acc;
+}
+
+// ---------------------------------------------------------------------------------------------
+// a7 generic: one thread per (sample, output 4-column chunk); stores of a warp are contiguous.
+// Four items per thread are in flight together (ids first, then rows, then stores).
+// ---------------------------------------------------------------------------------------------
+template <bool PARTIAL>
+__global__ void __launch_bounds__(256) lookup_items_kernel(const FieldDev* __restrict__ fields,
+                                                          const int32_t* __restrict__ chunk_field,
+                                                          const int32_t* __restrict__ chunk_q, int32_t n_chunks,
+                                                          int32_t n_fields, const int32_t* __restrict__ ids,
+                                                          int64_t ids_ld, int64_t batch, float* __restrict__ out,
+                                                          int64_t out_ld, float* __restrict__ aux,
+                                                          int32_t* __restrict__ oob) {
+  const int64_t total = batch * n_chunks;
+  for (int64_t item = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; item < total;
+       item += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = item / n_chunks;
+    const int c = (int)(item - b * n_chunks);
+    const int fi = __ldg(chunk_field + c);
+    const int q = __ldg(chunk_q + c);
+    const FieldDev f = fields[fi];
+    float n_valid;
+    const float4 r = pooled_chunk<PARTIAL>(f, ids + b * ids_ld, q, n_valid, oob, b);
+    stg_na(reinterpret_cast<float4*>(out + b * out_ld + f.out_col) + q, r);
+    if (aux != nullptr && q == 0) {
+      if (PARTIAL)
+        aux[b * n_fields + fi] = n_valid;
+      else
+        aux[b * n_fields + fi] = f.pool == HRB_POOL_MEAN ? (n_valid > 0.f ? __fdiv_rn(1.0f, n_valid) : 0.f) : 1.0f;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// a7 + a9 fused, uniform D: G = D/4 lanes own one sample and walk its F fields, so the FM sums
+// (sum_f x, sum_f x^2) stay in registers and the pooled (B,F,D) block is written exactly once.
+//   LEN1: every field is a plain lookup (Criteo shape) -> FU rows per lane in flight.
+// ---------------------------------------------------------------------------------------------
+template <int G, bool LEN1, bool FM>
+__global__ void __launch_bounds__(256) lookup_rows_kernel(const FieldDev* __restrict__ fields_g, int32_t n_fields,
+                                                         const int32_t* __restrict__ ids, int64_t ids_ld,
+                                                         int64_t batch, float* __restrict__ out, int64_t out_ld,
+                                                         float* __restrict__ inv_count,
+                                                         const float* __restrict__ fm_w,
+                                                         const float* __restrict__ fm_w0,
+                                                         float* __restrict__ fm_out, float* __restrict__ fm_sum,
+                                                         int32_t* __restrict__ oob) {
+  constexpr int SPB = 256 / G;  // samples per block pass
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  FieldDev* fields = reinterpret_cast<FieldDev*>(smem_raw);  // descriptors are read F times per sample
+  for (int i = threadIdx.x; i < n_fields * (int)(sizeof(FieldDev) / 4); i += blockDim.x)
+    reinterpret_cast<uint32_t*>(fields)[i] = reinterpret_cast<const uint32_t*>(fields_g)[i];
+  __syncthreads();
+  const int q = threadIdx.x % G;
+  const int s_in_block = threadIdx.x / G;
+  float4 w4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  float w0 = 0.f;
+  if (FM) {
+    w4 = __ldg(reinterpret_cast<const float4*>(fm_w) + q);
+    w0 = __ldg(fm_w0);
+  }
+  for (int64_t b = blockIdx.x * (int64_t)SPB + s_in_block; b < batch; b += (int64_t)gridDim.x * SPB) {
+    const int32_t* ids_row = ids + b * ids_ld;
+    float* out_row = out + b * out_ld;
+    float4 S = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 Q = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (LEN1) {
+      constexpr int FU = 13;
+      for (int f0 = 0; f0 < n_fields; f0 += FU) {
+        int32_t id[FU];
+        float4 v[FU];
+#pragma unroll
+        for (int u = 0; u < FU; ++u) id[u] = (f0 + u < n_fields) ? __ldg(ids_row + fields[f0 + u].ids_col) : 0;
+#pragma unroll
+        for (int u = 0; u < FU; ++u) {
+          v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (f0 + u < n_fields) {
+            const FieldDev& f = fields[f0 + u];
+            if (id[u] >= 0 && (int64_t)id[u] < f.rows) {
+              v[u] = ldg_nc_na(reinterpret_cast<const float4*>(f.table) + (int64_t)id[u] * G + q);
+            } else if (oob != nullptr) {
+              oob[0] = 1;
+              oob[1] = (int32_t)b;
+            }
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < FU; ++u) {
+          if (f0 + u < n_fields) {
+            stg_na(reinterpret_cast<float4*>(out_row + fields[f0 + u].out_col) + q, v[u]);
+            if (FM) {
+              S.x += v[u].x; S.y += v[u].y; S.z += v[u].z; S.w += v[u].w;
+              Q.x = fmaf(v[u].x, v[u].x, Q.x); Q.y = fmaf(v[u].y, v[u].y, Q.y);
+              Q.z = fmaf(v[u].z, v[u].z, Q.z); Q.w = fmaf(v[u].w, v[u].w, Q.w);
+            }
+          }
+        }
+      }
+      if (inv_count != nullptr)
+        for (int f = q; f < n_fields; f += G) inv_count[b * n_fields + f] = 1.0f;
+    } else {
+      for (int fi = 0; fi < n_fields; ++fi) {
+        const FieldDev f = fields[fi];
+        float n_valid;
+        const float4 r = pooled_chunk<false>(f, ids_row, q, n_valid, oob, b);
+        stg_na(reinterpret_cast<float4*>(out_row + f.out_col) + q, r);
+        if (inv_count != nullptr && q == 0)
+          inv_count[b * n_fields + fi] =
+              f.pool == HRB_POOL_MEAN ? (n_valid > 0.f ? __fdiv_rn(1.0f, n_valid) : 0.f) : 1.0f;
+        if (FM) {
+          S.x += r.x; S.y += r.y; S.z += r.z; S.w += r.w;
+          Q.x = fmaf(r.x, r.x, Q.x); Q.y = fmaf(r.y, r.y, Q.y);
+          Q.z = fmaf(r.z, r.z, Q.z); Q.w = fmaf(r.w, r.w, Q.w);
+        }
+      }
+    }
+    if (FM) {
+      // interaction.py:29-39: part2 = (sum_f x).w ; part3 = 0.5*sum_d[(sum_f x)^2 - sum_f x^2]
+      float p2 = S.x * w4.x + S.y * w4.y + S.z * w4.z + S.w * w4.w;
+      float p3 = (S.x * S.x - Q.x) + (S.y * S.y - Q.y) + (S.z * S.z - Q.z) + (S.w * S.w - Q.w);
+#pragma unroll
+      for (int o = G / 2; o > 0; o >>= 1) {
+        p2 += __shfl_xor_sync(0xffffffffu, p2, o, G);
+        p3 += __shfl_xor_sync(0xffffffffu, p3, o, G);
+      }
+      if (q == 0) fm_out[b] = p2 + 0.5f * p3 + w0;
+      if (fm_sum != nullptr) reinterpret_cast<float4*>(fm_sum + b * (int64_t)(G * 4))[q] = S;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// (e) sharding helpers
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) shard_ids_kernel(const FieldDev* __restrict__ fields,
+                                                       const int32_t* __restrict__ pos_field, int32_t pos_cols,
+                                                       const int32_t* __restrict__ ids, int64_t ids_ld,
+                                                       int64_t batch, int32_t n_ranks,
+                                                       int32_t* __restrict__ send) {
+  // send[r, b, c] over the dense position columns c (pos space), r = destination rank
+  const int64_t total = batch * pos_cols;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = i / pos_cols;
+    const int c = (int)(i - b * pos_cols);
+    const FieldDev& f = fields[pos_field[c]];
+    const int32_t id = ids[b * ids_ld + f.ids_col + (c - f.pos_col)];
+    const bool valid = (f.pool == HRB_POOL_NONE || id != 0) && id >= 0;
+    const int owner = valid ? id % n_ranks : -1;
+    const int32_t local = valid ? id / n_ranks : 0;
+    for (int r = 0; r < n_ranks; ++r)
+      send[((int64_t)r * batch + b) * pos_cols + c] = (r == owner) ? local : (int32_t)kNotMine;
+  }
+}
+
+__global__ void __launch_bounds__(256) lookup_combine_kernel(const FieldDev* __restrict__ fields,
+                                                            const int32_t* __restrict__ chunk_field,
+                                                            const int32_t* __restrict__ chunk_q,
+                                                            int32_t n_chunks, int32_t n_fields,
+                                                            const float* __restrict__ psum,
+                                                            const float* __restrict__ pcount, int32_t n_ranks,
+                                                            int64_t batch, int64_t out_ld,
+                                                            float* __restrict__ out,
+                                                            float* __restrict__ inv_count) {
+  const int64_t total = batch * n_chunks;
+  for (int64_t item = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; item < total;
+       item += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = item / n_chunks;
+    const int c = (int)(item - b * n_chunks);
+    const int fi = chunk_field[c];
+    const int q = chunk_q[c];
+    const FieldDev& f = fields[fi];
+    float4 acc = f.pool == HRB_POOL_MAX ? make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY)
+                                        : make_float4(0.f, 0.f, 0.f, 0.f);
+    float cnt = 0.f;
+    for (int r = 0; r < n_ranks; ++r) {  // fixed rank order -> deterministic
+      const float4 v = *(reinterpret_cast<const float4*>(psum + ((int64_t)r * batch + b) * out_ld + f.out_col) + q);
+      const float n = pcount[((int64_t)r * batch + b) * n_fields + fi];
+      cnt += n;
+      if (f.pool == HRB_POOL_MAX) {
+        if (n > 0.f) {
+          acc.x = fmaxf(acc.x, v.x); acc.y = fmaxf(acc.y, v.y);
+          acc.z = fmaxf(acc.z, v.z); acc.w = fmaxf(acc.w, v.w);
+        }
+      } else {
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
+    }
+    if (f.pool == HRB_POOL_MEAN) {
+      const float w = cnt > 0.f ? __fdiv_rn(1.0f, cnt) : 0.0f;
+      acc.x *= w; acc.y *= w; acc.z *= w; acc.w *= w;
+    } else if (f.pool == HRB_POOL_MAX && cnt < (float)f.seq_len) {
+      // padded positions: -1e9 (row 0 of a |w|<32 table rounds away), see pooled_chunk
+      acc.x = fmaxf(acc.x, -1e9f); acc.y = fmaxf(acc.y, -1e9f);
+      acc.z = fmaxf(acc.z, -1e9f); acc.w = fmaxf(acc.w, -1e9f);
+    }
+    *(reinterpret_cast<float4*>(out + b * out_ld + f.out_col) + q) = acc;
+    if (inv_count != nullptr && q == 0)
+      inv_count[b * n_fields + fi] = f.pool == HRB_POOL_MEAN ? (cnt > 0.f ? __fdiv_rn(1.0f, cnt) : 0.f) : 1.0f;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// a13 backward.  Step 1: keys.  One thread per (sample, field): key = key_base(table) + id for
+// every valid position, SENTINEL (= total rows, sorts last) for padding; scale = 1/n_valid (mean).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) bwd_keys_kernel(const FieldDev* __restrict__ fields, int32_t n_fields,
+                                                      int32_t pos_cols, const int32_t* __restrict__ ids,
+                                                      int64_t ids_ld, int64_t batch, uint32_t sentinel,
+                                                      uint32_t* __restrict__ keys, uint32_t* __restrict__ vals,
+                                                      float* __restrict__ scale) {
+  const int64_t total = batch * n_fields;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = i / n_fields;
+    const int fi = (int)(i - b * n_fields);
+    const FieldDev& f = fields[fi];
+    const int32_t* idp = ids + b * ids_ld + f.ids_col;
+    const int64_t p0 = b * pos_cols + f.pos_col;
+    int cnt = 0;
+    for (int l = 0; l < f.seq_len; ++l) {
+      const int32_t id = idp[l];
+      const bool valid = (f.pool == HRB_POOL_NONE || id != 0) && id >= 0 && (int64_t)id < f.rows;
+      cnt += valid;
+      keys[p0 + l] = valid ? f.key_base + (uint32_t)id : sentinel;
+      vals[p0 + l] = (uint32_t)(p0 + l);
+    }
+    scale[i] = f.pool == HRB_POOL_MEAN ? (cnt > 0 ? __fdiv_rn(1.0f, (float)cnt) : 0.f) : 1.0f;
+  }
+}
+
+__global__ void __launch_bounds__(256) flat_keys_kernel(const int32_t* __restrict__ ids, int64_t n, int64_t vocab,
+                                                       uint32_t sentinel, uint32_t* __restrict__ keys,
+                                                       uint32_t* __restrict__ vals) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int32_t id = ids[i];
+    keys[i] = (id >= 0 && id < vocab) ? (uint32_t)id : sentinel;
+    vals[i] = (uint32_t)i;
+  }
+}
+
+// gradient sources -----------------------------------------------------------------------------
+struct PlanGrad {  // gradient of position p comes from dout[b, out_col_f : +D] * scale[b,f]
+  const FieldDev* fields;
+  const int32_t* pos_field;
+  const float* dout;
+  const float* scale;
+  int64_t dout_ld;
+  int32_t pos_cols, n_fields;
+  __device__ __forceinline__ float4 load(uint32_t p, int q, float& s) const {
+    const int64_t b = p / (uint32_t)pos_cols;
+    const int c = (int)(p - (uint32_t)b * (uint32_t)pos_cols);
+    const int fi = __ldg(pos_field + c);
+    s = __ldg(scale + b * n_fields + fi);
+    if (q * 4 >= fields[fi].dim) return make_float4(0.f, 0.f, 0.f, 0.f);  // narrower table than the widest one
+    return __ldg(reinterpret_cast<const float4*>(dout + b * dout_ld + fields[fi].out_col) + q);
+  }
+};
+struct FlatGrad {  // gradient of position p is dout[p, :]
+  const float* dout;
+  int32_t dim;
+  __device__ __forceinline__ float4 load(uint32_t p, int q, float& s) const {
+    s = 1.0f;
+    return __ldg(reinterpret_cast<const float4*>(dout + (int64_t)p * dim) + q);
+  }
+};
+
+// row updates ----------------------------------------------------------------------------------
+struct ApplyCtx {
+  const TableDev* tables;
+  int32_t n_tables;
+  hrb_opt_params opt;
+  float* dense_out;  // for the dense-gradient face
+  float lr_t;        // adam: lr*sqrt(bc2)/bc1
+};
+
+__device__ __forceinline__ int find_table(const TableDev* __restrict__ t, int n, uint32_t key) {
+  int lo = 0, hi = n - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (t[mid].key_base <= key) lo = mid; else hi = mid - 1;
+  }
+  return lo;
+}
+
+template <int MODE>  // 0 sgd, 1 adam lazy, 2 dense gradient add
+__device__ __forceinline__ void apply_row(const ApplyCtx& c, uint32_t key, int q, float4 g) {
+  if (MODE == 2) {
+    float4* p = reinterpret_cast<float4*>(c.dense_out + (int64_t)key * c.tables[0].dim) + q;
+    float4 o = *p;
+    o.x += g.x; o.y += g.y; o.z += g.z; o.w += g.w;
+    *p = o;
+    return;
+  }
+  const int ti = find_table(c.tables, c.n_tables, key);
+  const TableDev& t = c.tables[ti];
+  if (q * 4 >= t.dim) return;
+  const int64_t off = (int64_t)(key - t.key_base) * (t.dim >> 2) + q;
+  float4* wp = reinterpret_cast<float4*>(t.w) + off;
+  float4 w = *wp;
+  const float l2 = c.opt.l2_scale;
+  g.x = fmaf(l2, w.x, g.x); g.y = fmaf(l2, w.y, g.y); g.z = fmaf(l2, w.z, g.z); g.w = fmaf(l2, w.w, g.w);
+  if (MODE == 0) {
+    const float lr = c.opt.lr;
+    w.x -= lr * g.x; w.y -= lr * g.y; w.z -= lr * g.z; w.w -= lr * g.w;
+  } else {
+    float4* mp = reinterpret_cast<float4*>(t.m) + off;
+    float4* vp = reinterpret_cast<float4*>(t.v) + off;
+    float4 m = *mp, v = *vp;
+    const float b1 = c.opt.beta1, b2 = c.opt.beta2, e = c.opt.eps, lr = c.lr_t;
+    m.x = b1 * m.x + (1.f - b1) * g.x; m.y = b1 * m.y + (1.f - b1) * g.y;
+    m.z = b1 * m.z + (1.f - b1) * g.z; m.w = b1 * m.w + (1.f - b1) * g.w;
+    v.x = b2 * v.x + (1.f - b2) * g.x * g.x; v.y = b2 * v.y + (1.f - b2) * g.y * g.y;
+    v.z = b2 * v.z + (1.f - b2) * g.z * g.z; v.w = b2 * v.w + (1.f - b2) * g.w * g.w;
+    w.x -= lr * m.x / (sqrtf(v.x) + e); w.y -= lr * m.y / (sqrtf(v.y) + e);
+    w.z -= lr * m.z / (sqrtf(v.z) + e); w.w -= lr * m.w / (sqrtf(v.w) + e);
+    *mp = m;
+    *vp = v;
+  }
+  *wp = w;
+}
+
+// Step 3: chunk kernel.  G lanes own CH consecutive sorted positions.  Runs (equal keys) that lie
+// strictly inside the chunk are final and update their row at once; the (at most two) runs that
+// touch a chunk edge and continue across it go to the partial buffer (slot 0 = head, 1 = tail).
+constexpr int CH = 16;
+constexpr uint32_t PF_VALID = 1u, PF_CONT = 2u, PF_ROPEN = 4u;
+
+template <int MODE, typename GradSrc>
+__global__ void __launch_bounds__(256) bwd_chunk_kernel(const uint32_t* __restrict__ keys,
+                                                       const uint32_t* __restrict__ vals, int64_t n,
+                                                       uint32_t sentinel, int G, GradSrc src, ApplyCtx ctx,
+                                                       float* __restrict__ partial /* (2*chunks, G*4) */,
+                                                       uint32_t* __restrict__ pkey, uint32_t* __restrict__ pflag) {
+  const int groups_per_block = blockDim.x / G;
+  const int q = threadIdx.x % G;
+  const int g_in_block = threadIdx.x / G;
+  if (g_in_block >= groups_per_block) return;
+  const int64_t n_chunks = (n + CH - 1) / CH;
+  for (int64_t chunk = blockIdx.x * (int64_t)groups_per_block + g_in_block; chunk < n_chunks;
+       chunk += (int64_t)gridDim.x * groups_per_block) {
+    const int64_t i0 = chunk * CH;
+    uint32_t k[CH];
+    float4 g[CH];
+#pragma unroll
+    for (int j = 0; j < CH; ++j) k[j] = (i0 + j < n) ? __ldg(keys + i0 + j) : sentinel;
+#pragma unroll
+    for (int j = 0; j < CH; ++j) {
+      g[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (k[j] != sentinel) {
+        float s;
+        const float4 v = src.load(__ldg(vals + i0 + j), q, s);
+        g[j] = make_float4(v.x * s, v.y * s, v.z * s, v.w * s);
+      }
+    }
+    const uint32_t kprev = i0 > 0 ? __ldg(keys + i0 - 1) : sentinel;
+    const uint32_t knext = (i0 + CH < n) ? __ldg(keys + i0 + CH) : sentinel;
+    if (q == 0) {
+      pflag[2 * chunk] = 0;
+      pflag[2 * chunk + 1] = 0;
+    }
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    int run_start = 0;
+#pragma unroll
+    for (int j = 0; j < CH; ++j) {
+      acc.x += g[j].x; acc.y += g[j].y; acc.z += g[j].z; acc.w += g[j].w;
+      const bool last = (j == CH - 1);
+      const uint32_t kn = last ? knext : k[j + 1];
+      if (last || kn != k[j]) {  // run [run_start, j] ends here (inside this chunk)
+        if (k[j] != sentinel) {
+          const bool lopen = (run_start == 0) && (i0 > 0) && (kprev == k[j]);
+          const bool ropen = last && (kn == k[j]);
+          if (!lopen && !ropen) {
+            apply_row<MODE>(ctx, k[j], q, acc);
+          } else {
+            const int slot = (run_start == 0) ? 0 : 1;
+            reinterpret_cast<float4*>(partial + (2 * chunk + slot) * (int64_t)(G * 4))[q] = acc;
+            if (q == 0) {
+              pkey[2 * chunk + slot] = k[j];
+              pflag[2 * chunk + slot] = PF_VALID | (lopen ? PF_CONT : 0u) | (ropen ? PF_ROPEN : 0u);
+            }
+          }
+        }
+        acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        run_start = j + 1;
+      }
+    }
+  }
+}
+
+// Step 4: merge kernel.  A partial that does not continue a previous chunk starts a chain; its group
+// walks the head slots of the following chunks in order (fixed order -> deterministic) and updates the row.
+template <int MODE>
+__global__ void __launch_bounds__(256) bwd_merge_kernel(int64_t n_chunks, int G, ApplyCtx ctx,
+                                                       const float* __restrict__ partial,
+                                                       const uint32_t* __restrict__ pkey,
+                                                       const uint32_t* __restrict__ pflag) {
+  const int groups_per_block = blockDim.x / G;
+  const int q = threadIdx.x % G;
+  const int g_in_block = threadIdx.x / G;
+  if (g_in_block >= groups_per_block) return;
+  const int64_t n_slots = 2 * n_chunks;
+  for (int64_t slot = blockIdx.x * (int64_t)groups_per_block + g_in_block; slot < n_slots;
+       slot += (int64_t)gridDim.x * groups_per_block) {
+    const uint32_t fl = __ldg(pflag + slot);
+    if (!(fl & PF_VALID) || (fl & PF_CONT)) continue;
+    float4 acc = reinterpret_cast<const float4*>(partial + slot * (int64_t)(G * 4))[q];
+    if (fl & PF_ROPEN) {
+      for (int64_t c = slot / 2 + 1; c < n_chunks; ++c) {
+        const uint32_t f2 = __ldg(pflag + 2 * c);
+        const float4 v = reinterpret_cast<const float4*>(partial + (2 * c) * (int64_t)(G * 4))[q];
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        if (!(f2 & PF_ROPEN)) break;
+      }
+    }
+    apply_row<MODE>(ctx, __ldg(pkey + slot), q, acc);
+  }
+}
+
+__global__ void __launch_bounds__(256) dense_grad_init_kernel(const float* __restrict__ table, float l2_scale,
+                                                             int64_t n, float* __restrict__ dtable) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    dtable[i] = table != nullptr ? l2_scale * table[i] : 0.0f;
+}
+
+static inline unsigned grid_for(int64_t work_items, int threads, int waves = 8) {
+  int64_t blocks = (work_items + threads - 1) / threads;
+  const int64_t cap = (int64_t)sm_count() * waves;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (unsigned)blocks;
+}
+
+static inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+struct BwdWorkspace {
+  uint32_t *keys_in, *keys_out, *vals_in, *vals_out, *pkey, *pflag;
+  float *scale, *partial;
+  void* cub_tmp;
+  size_t cub_bytes;
+  size_t total;
+};
+
+static int carve_bwd_ws(int64_t n, int64_t scale_elems, int max_dim, int key_bits, void* base, BwdWorkspace& w) {
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    void* p = base ? (void*)((char*)base + off) : nullptr;
+    off += align_up(bytes);
+    return p;
+  };
+  const int64_t n_chunks = (n + CH - 1) / CH;
+  w.keys_in = (uint32_t*)take((size_t)n * 4);
+  w.keys_out = (uint32_t*)take((size_t)n * 4);
+  w.vals_in = (uint32_t*)take((size_t)n * 4);
+  w.vals_out = (uint32_t*)take((size_t)n * 4);
+  w.scale = (float*)take((size_t)scale_elems * 4);
+  w.partial = (float*)take((size_t)n_chunks * 2 * max_dim * 4);
+  w.pkey = (uint32_t*)take((size_t)n_chunks * 2 * 4);
+  w.pflag = (uint32_t*)take((size_t)n_chunks * 2 * 4);
+  size_t cub_bytes = 0;
+  cudaError_t e = cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr,
+                                                  (const uint32_t*)nullptr, (uint32_t*)nullptr, (int)n, 0, key_bits);
+  if (e != cudaSuccess) return fail(HRB_CUDA_ERROR, "cub temp size query: %s", cudaGetErrorString(e));
+  w.cub_bytes = cub_bytes;
+  w.cub_tmp = take(cub_bytes);
+  w.total = off;
+  return HRB_OK;
+}
+
+static int bits_for(uint64_t max_value) {
+  int b = 1;
+  while (b < 32 && (max_value >> b) != 0) ++b;
+  return b;
+}
+
+template <typename GradSrc>
+static int run_sorted_update(int mode, const BwdWorkspace& w, int64_t n, uint32_t sentinel, int key_bits, int G,
+                             GradSrc src, ApplyCtx ctx, cudaStream_t st) {
+  size_t cub_bytes = w.cub_bytes;
+  HRB_CUDA(cub::DeviceRadixSort::SortPairs(w.cub_tmp, cub_bytes, w.keys_in, w.keys_out, w.vals_in, w.vals_out,
+                                           (int)n, 0, key_bits, st));
+  const int64_t n_chunks = (n + CH - 1) / CH;
+  const int threads = 256;
+  const int gpb = threads / G;
+  const unsigned grid1 = grid_for(n_chunks * G, gpb * G, 16);
+  const unsigned grid2 = grid_for(2 * n_chunks * G, gpb * G, 16);
+  const int launch_threads = gpb * G;
+#define HRB_RUN_MODE(M)                                                                                        \
+  bwd_chunk_kernel<M, GradSrc><<<grid1, launch_threads, 0, st>>>(w.keys_out, w.vals_out, n, sentinel, G, src, \
+                                                                 ctx, w.partial, w.pkey, w.pflag);            \
+  HRB_LAUNCH_CHECK();                                                                                          \
+  bwd_merge_kernel<M><<<grid2, launch_threads, 0, st>>>(n_chunks, G, ctx, w.partial, w.pkey, w.pflag);         \
+  HRB_LAUNCH_CHECK();
+  if (mode == 0) {
+    HRB_RUN_MODE(0)
+  } else if (mode == 1) {
+    HRB_RUN_MODE(1)
+  } else {
+    HRB_RUN_MODE(2)
+  }
+#undef HRB_RUN_MODE
+  return HRB_OK;
+}
+
+}  // namespace hrb
+
+using namespace hrb;
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+HRB_API int hrb_embedding_fwd(const float* table, int64_t vocab, int32_t dim, const int32_t* ids, int64_t n_ids,
+                              float* out, uint8_t* mask, int32_t* oob, void* stream) {
+  HRB_REQUIRE(table && ids && out && vocab > 0 && dim > 0 && n_ids >= 0, "hrb_embedding_fwd: null/negative argument");
+  if (dim % 4 != 0) return fail(HRB_UNSUPPORTED, "hrb_embedding_fwd: dim %d is not a multiple of 4", dim);
+  HRB_REQUIRE(aligned16(table) && aligned16(out), "hrb_embedding_fwd: table/out must be 16-byte aligned");
+  HRB_REQUIRE(mask == nullptr || (reinterpret_cast<uintptr_t>(mask) & 3u) == 0, "hrb_embedding_fwd: mask must be 4-byte aligned");
+  if (n_ids == 0) return HRB_OK;
+  const int chunks = dim / 4;
+  const unsigned grid = grid_for((n_ids * chunks + 3) / 4, 256, 8);
+  embedding_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(table, vocab, chunks, ids, n_ids, out, mask, oob);
+  HRB_LAUNCH_CHECK();
+  return HRB_OK;
+}
+
+HRB_API int hrb_seq_pool_fwd(const float* x, const uint8_t* mask, int64_t batch, int32_t seq_len, int32_t dim,
+                             int32_t method, float* out, void* stream) {
+  HRB_REQUIRE(x && out && batch >= 0 && seq_len > 0 && dim > 0, "hrb_seq_pool_fwd: null/negative argument");
+  HRB_REQUIRE(mask != nullptr, "hrb_seq_pool_fwd: mask is NULL (Embedding layer should set `mask_zero` as True)");
+  HRB_REQUIRE(method == HRB_POOL_MEAN || method == HRB_POOL_SUM || method == HRB_POOL_MAX,
+              "hrb_seq_pool_fwd: Pooling method should be `mean`, `max`, or `sum`");
+  if (batch == 0) return HRB_OK;
+  seq_pool_fwd_kernel<<<grid_for(batch * dim, 256), 256, 0, (cudaStream_t)stream>>>(x, mask, batch, seq_len, dim,
+                                                                                    method, out);
+  HRB_LAUNCH_CHECK();
+  return HRB_OK;
+}
+
+HRB_API int hrb_seq_pool_bwd(const float* x, const uint8_t* mask, const float* dout, int64_t batch, int32_t seq_len,
+                             int32_t dim, int32_t method, float* dx, void* stream) {
+  HRB_REQUIRE(x && mask && dout && dx && batch >= 0 && seq_len > 0 && dim > 0, "hrb_seq_pool_bwd: null/negative argument");
+  HRB_REQUIRE(method == HRB_POOL_MEAN || method == HRB_POOL_SUM || method == HRB_POOL_MAX,
+              "hrb_seq_pool_bwd: Pooling method should be `mean`, `max`, or `sum`");
+  if (batch == 0) return HRB_OK;
+  seq_pool_bwd_kernel<<<grid_for(batch * dim, 256), 256, 0, (cudaStream_t)stream>>>(x, mask, dout, batch, seq_len,
+                                                                                    dim, method, dx);
+  HRB_LAUNCH_CHECK();
+  return HRB_OK;
+}
+
+HRB_API int hrb_plan_create(const hrb_table_desc* tables_host, int32_t n_tables, const hrb_field_desc* fields_host,
+                            int32_t n_fields, hrb_plan** plan_out) {
+  HRB_REQUIRE(tables_host && fields_host && plan_out && n_tables > 0 && n_fields > 0, "hrb_plan_create: null/empty argument");
+  hrb_plan* p = new (std::nothrow) hrb_plan();
+  HRB_REQUIRE(p != nullptr, "hrb_plan_create: out of host memory");
+  p->n_tables = n_tables;
+  p->n_fields = n_fields;
+  p->tables.assign(tables_host, tables_host + n_tables);
+  p->fields.assign(fields_host, fields_host + n_fields);
+  uint64_t base = 0;
+  p->tdev_host.resize(n_tables);
+  for (int t = 0; t < n_tables; ++t) {
+    const hrb_table_desc& td = p->tables[t];
+    if (!td.weight || td.rows <= 0 || td.dim <= 0 || td.dim % 4 != 0 || !aligned16(td.weight) ||
+        (td.adam_m && !aligned16(td.adam_m)) || (td.adam_v && !aligned16(td.adam_v))) {
+      delete p;
+      return fail(td.dim % 4 ? HRB_UNSUPPORTED : HRB_BAD_ARG,
+                  "hrb_plan_create: table %d needs a 16-byte aligned weight, rows>0 and dim%%4==0 (dim=%d)", t, td.dim);
+    }
+    p->tdev_host[t] = TableDev{td.weight, td.adam_m, td.adam_v, td.rows, (uint32_t)base, td.dim};
+    base += (uint64_t)td.rows;
+    if (td.dim > p->max_dim) p->max_dim = td.dim;
+  }
+  if (base >= 0xFFFFFFFFull) {
+    delete p;
+    return fail(HRB_UNSUPPORTED, "hrb_plan_create: %llu total rows do not fit 32-bit sort keys", (unsigned long long)base);
+  }
+  p->total_rows = base;
+  p->key_bits = bits_for(base);
+  p->fdev_host.resize(n_fields);
+  std::vector<int32_t> chunk_field, chunk_q, pos_field;
+  const int32_t dim0 = p->tables[p->fields[0].table < n_tables && p->fields[0].table >= 0 ? p->fields[0].table : 0].dim;
+  for (int f = 0; f < n_fields; ++f) {
+    const hrb_field_desc& fd = p->fields[f];
+    if (fd.table < 0 || fd.table >= n_tables || fd.seq_len <= 0 || fd.ids_col < 0 || fd.out_col < 0 ||
+        fd.out_col % 4 != 0 || fd.pool < HRB_POOL_NONE || fd.pool > HRB_POOL_MAX ||
+        (fd.pool == HRB_POOL_NONE && fd.seq_len != 1)) {
+      delete p;
+      return fail(HRB_BAD_ARG, "hrb_plan_create: field %d is malformed (table/seq_len/cols/pool)", f);
+    }
+    const TableDev& td = p->tdev_host[fd.table];
+    p->fdev_host[f] = FieldDev{td.w, td.rows, td.key_base, td.dim, fd.seq_len, fd.pool, fd.ids_col, fd.out_col,
+                               p->pos_cols, fd.table};
+    for (int l = 0; l < fd.seq_len; ++l) pos_field.push_back(f);
+    p->pos_cols += fd.seq_len;
+    for (int q = 0; q < td.dim / 4; ++q) {
+      chunk_field.push_back(f);
+      chunk_q.push_back(q);
+    }
+    if (td.dim != dim0) p->uniform_dim = false;
+    if (fd.out_col != p->fields[0].out_col + f * dim0) p->contiguous_out = false;
+    if (fd.seq_len != 1 || fd.pool != HRB_POOL_NONE) p->all_len1 = false;
+    if (fd.pool == HRB_POOL_MAX) p->has_max = true;
+  }
+  if (!p->uniform_dim) p->contiguous_out = false;
+  p->out_chunks = (int32_t)chunk_field.size();
+  // one device blob: fields | tables | chunk_field | chunk_q | pos_field
+  const size_t sz_f = align_up(sizeof(FieldDev) * n_fields), sz_t = align_up(sizeof(TableDev) * n_tables);
+  const size_t sz_c = align_up(sizeof(int32_t) * chunk_field.size()), sz_p = align_up(sizeof(int32_t) * pos_field.size());
+  const size_t total = sz_f + sz_t + 2 * sz_c + sz_p;
+  std::vector<char> blob(total, 0);
+  memcpy(blob.data(), p->fdev_host.data(), sizeof(FieldDev) * n_fields);
+  memcpy(blob.data() + sz_f, p->tdev_host.data(), sizeof(TableDev) * n_tables);
+  memcpy(blob.data() + sz_f + sz_t, chunk_field.data(), sizeof(int32_t) * chunk_field.size());
+  memcpy(blob.data() + sz_f + sz_t + sz_c, chunk_q.data(), sizeof(int32_t) * chunk_q.size());
+  memcpy(blob.data() + sz_f + sz_t + 2 * sz_c, pos_field.data(), sizeof(int32_t) * pos_field.size());
+  cudaError_t e = cudaMalloc(&p->dev_blob, total);
+  if (e == cudaSuccess) e = cudaMemcpy(p->dev_blob, blob.data(), total, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    if (p->dev_blob) cudaFree(p->dev_blob);
+    delete p;
+    return fail(HRB_CUDA_ERROR, "hrb_plan_create: %s", cudaGetErrorString(e));
+  }
+  char* d = (char*)p->dev_blob;
+  p->d_fields = (FieldDev*)d;
+  p->d_tables = (TableDev*)(d + sz_f);
+  p->d_chunk_field = (int32_t*)(d + sz_f + sz_t);
+  p->d_chunk_q = (int32_t*)(d + sz_f + sz_t + sz_c);
+  p->d_pos_field = (int32_t*)(d + sz_f + sz_t + 2 * sz_c);
+  *plan_out = p;
+  return HRB_OK;
+}
+
+HRB_API int hrb_plan_destroy(hrb_plan* plan) {
+  if (plan == nullptr) return HRB_OK;
+  if (plan->dev_blob) cudaFree(plan->dev_blob);
+  delete plan;
+  return HRB_OK;
+}
+
+static int check_lookup_args(const char* who, const hrb_plan* plan, const int32_t* ids, int64_t ids_ld, int64_t batch,
+                             const float* out, int64_t out_ld) {
+  HRB_REQUIRE(plan && ids && out && batch >= 0, "%s: null/negative argument", who);
+  HRB_REQUIRE(aligned16(out) && out_ld % 4 == 0, "%s: out must be 16-byte aligned with out_ld %% 4 == 0", who);
+  for (const auto& f : plan->fdev_host) {
+    HRB_REQUIRE(f.ids_col + f.seq_len <= ids_ld, "%s: ids_ld %lld too small for a field ending at column %d", who,
+                (long long)ids_ld, f.ids_col + f.seq_len);
+    HRB_REQUIRE(f.out_col + f.dim <= out_ld, "%s: out_ld %lld too small for a field ending at column %d", who,
+                (long long)out_ld, f.out_col + f.dim);
+  }
+  return HRB_OK;
+}
+
+template <bool FM>
+static int launch_rows(const hrb_plan* plan, const int32_t* ids, int64_t ids_ld, int64_t batch, float* out,
+                       int64_t out_ld, float* inv_count, const float* fm_w, const float* fm_w0, float* fm_out,
+                       float* fm_sum, int32_t* oob, cudaStream_t st) {
+  const int G = plan->max_dim / 4;
+  const int spb = 256 / G;
+  // enough CTAs for every SM to hold its full complement, persistent-style grid-stride over samples
+  int64_t blocks = (batch + spb - 1) / spb;
+  const int64_t cap = (int64_t)sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  const size_t smem = sizeof(FieldDev) * (size_t)plan->n_fields;
+  if (smem > 40 * 1024) return fail(HRB_UNSUPPORTED, "fused row kernel: too many fields (%d)", plan->n_fields);
+#define HRB_ROWS(GG)                                                                                              \
+  if (plan->all_len1)                                                                                             \
+    lookup_rows_kernel<GG, true, FM><<<(unsigned)blocks, 256, smem, st>>>(plan->d_fields, plan->n_fields, ids, ids_ld, \
+                                                                      batch, out, out_ld, inv_count, fm_w, fm_w0, \
+                                                                      fm_out, fm_sum, oob);                       \
+  else                                                                                                            \
+    lookup_rows_kernel<GG, false, FM><<<(unsigned)blocks, 256, smem, st>>>(plan->d_fields, plan->n_fields, ids,      \
+                                                                       ids_ld, batch, out, out_ld, inv_count,     \
+                                                                       fm_w, fm_w0, fm_out, fm_sum, oob);
+  switch (G) {
+    case 1: HRB_ROWS(1) break;
+    case 2: HRB_ROWS(2) break;
+    case 4: HRB_ROWS(4) break;
+    case 8: HRB_ROWS(8) break;
+    case 16: HRB_ROWS(16) break;
+    case 32: HRB_ROWS(32) break;
+    default: return fail(HRB_UNSUPPORTED, "fused row kernel needs dim/4 in {1,2,4,8,16,32}, got dim=%d", plan->max_dim);
+  }
+#undef HRB_ROWS
+  HRB_LAUNCH_CHECK();
+  return HRB_OK;
+}
+
+HRB_API int hrb_lookup_fwd(const hrb_plan* plan, const int32_t* ids, int64_t ids_ld, int64_t batch, float* out,
+                           int64_t out_ld, float* inv_count, int32_t* oob, void* stream) {
+  int rc = check_lookup_args("hrb_lookup_fwd", plan, ids, ids_ld, batch, out, out_ld);
+  if (rc != HRB_OK) return rc;
+  if (batch == 0) return HRB_OK;
+  const unsigned grid = grid_for(batch * plan->out_chunks, 256, 8);
+  lookup_items_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(plan->d_fields, plan->d_chunk_field,
+                                                                    plan->d_chunk_q, plan->out_chunks, plan->n_fields,
+                                                                    ids, ids_ld, batch, out, out_ld, inv_count, oob);
+  HRB_LAUNCH_CHECK();
+  return HRB_OK;
+}
+
+HRB_API int hrb_lookup_fm_fwd(const hrb_plan* plan, const int32_t* ids, int64_t ids_ld, int64_t batch, float* out,
+                              int64_t out_ld, float* inv_count, const float* fm_w, const float* fm_w0, float* fm_out,
+                              float* fm_sum, int32_t* oob, void* stream) {
+  int rc = check_lookup_args("hrb_lookup_fm_fwd", plan, ids, ids_ld, batch, out, out_ld);
+  if (rc != HRB_OK) return rc;
+  HRB_REQUIRE(fm_w && fm_w0 && fm_out, "hrb_lookup_fm_fwd: fm_w / fm_w0 / fm_out is NULL");
+  HRB_REQUIRE(aligned16(fm_w) && (fm_sum == nullptr || aligned16(fm_sum)), "hrb_lookup_fm_fwd: fm_w/fm_sum must be 16-byte aligned");
+  if (!plan->uniform_dim)
+    return fail(HRB_UNSUPPORTED, "hrb_lookup_fm_fwd: FM needs every field to have the same embedding dim");
+  if (batch == 0) return HRB_OK;
+  return launch_rows<true>(plan, ids, ids_ld, batch, out, out_ld, inv_count, fm_w, fm_w0, fm_out, fm_sum, oob,
+                           (cudaStream_t)stream);
+}
+
+HRB_API int hrb_lookup_bwd_workspace(const hrb_plan* plan, int64_t ids_ld, int64_t batch, size_t* bytes) {
+  HRB_REQUIRE(plan && bytes && batch >= 0, "hrb_lookup_bwd_workspace: null/negative argument");
+  (void)ids_ld;
+  const int64_t n = batch * plan->pos_cols;
+  HRB_REQUIRE(n < 0x7FFFFFFFll, "hrb_lookup_bwd_workspace: batch*sum(seq_len) = %lld exceeds 2^31-1", (long long)n);
+  BwdWorkspace w;
+  int rc = carve_bwd_ws(n > 0 ? n : 1, batch * plan->n_fields + 1, plan->max_dim, plan->key_bits, nullptr, w);
+  if (rc != HRB_OK) return rc;
+  *bytes = w.total;
+  return HRB_OK;
+}
+
+HRB_API int hrb_lookup_bwd_update(const hrb_plan* plan, const int32_t* ids, int64_t ids_ld, int64_t batch,
+                                  const float* dout, int64_t dout_ld, const float* inv_count,
+                                  const hrb_opt_params* opt_host, void* workspace, size_t workspace_bytes,
+                                  void* stream) {
+  (void)inv_count;  // recomputed from ids; accepted for symmetry with the forward
+  HRB_REQUIRE(plan && ids && dout && opt_host && workspace && batch >= 0, "hrb_lookup_bwd_update: null/negative argument");
+  HRB_REQUIRE(aligned16(dout) && dout_ld % 4 == 0, "hrb_lookup_bwd_update: dout must be 16-byte aligned, dout_ld %% 4 == 0");
+  if (plan->has_max)
+    return fail(HRB_UNSUPPORTED, "hrb_lookup_bwd_update: max-pooled fields go through hrb_seq_pool_bwd + hrb_embedding_bwd_dense");
+  HRB_REQUIRE(opt_host->opt == HRB_OPT_SGD || opt_host->opt == HRB_OPT_ADAM_LAZY, "hrb_lookup_bwd_update: unknown optimiser %d", opt_host->opt);
+  if (opt_host->opt == HRB_OPT_ADAM_LAZY)
+    for (const auto& t : plan->tdev_host)
+      HRB_REQUIRE(t.m && t.v, "hrb_lookup_bwd_update: lazy Adam needs adam_m/adam_v for every table");
+  const int G = plan->max_dim / 4;
+  if (G > 256) return fail(HRB_UNSUPPORTED, "hrb_lookup_bwd_update: dim %d too large", plan->max_dim);
+  if (batch == 0) return HRB_OK;
+  const int64_t n = batch * plan->pos_cols;
+  HRB_REQUIRE(n < 0x7FFFFFFFll, "hrb_lookup_bwd_update: batch*sum(seq_len) exceeds 2^31-1");
+  BwdWorkspace w;
+  int rc = carve_bwd_ws(n, batch * plan->n_fields + 1, plan->max_dim, plan->key_bits, workspace, w);
+  if (rc != HRB_OK) return rc;
+  if (w.total > workspace_bytes)
+    return fail(HRB_WORKSPACE, "hrb_lookup_bwd_update: workspace %zu < required %zu bytes", workspace_bytes, w.total);
+  cudaStream_t st = (cudaStream_t)stream;
+  const uint32_t sentinel = (uint32_t)plan->total_rows;
+  bwd_keys_kernel<<<grid_for(batch * plan->n_fields, 256), 256, 0, st>>>(plan->d_fields, plan->n_fields, plan->pos_cols,
+                                                                        ids, ids_ld, batch, sentinel, w.keys_in,
+                                                                        w.vals_in, w.scale);
+  HRB_LAUNCH_CHECK();
+  PlanGrad src{plan->d_fields, plan->d_pos_field, dout, w.scale, dout_ld, plan->pos_cols, plan->n_fields};
+  ApplyCtx ctx{plan->d_tables, plan->n_tables, *opt_host, nullptr, 0.f};
+  if (opt_host->opt == HRB_OPT_ADAM_LAZY)
+    ctx.lr_t = opt_host->lr * sqrtf(opt_host->bias_corr2) / opt_host->bias_corr1;
+  return run_sorted_update(opt_host->opt == HRB_OPT_SGD ? 0 : 1, w, n, sentinel, plan->key_bits, G, src, ctx, st);
+}
+
+HRB_API int hrb_embedding_bwd_dense_workspace(int64_t n_ids, int32_t dim, size_t* bytes) {
+  HRB_REQUIRE(bytes && n_ids >= 0 && dim > 0, "hrb_embedding_bwd_dense_workspace: bad argument");
+  HRB_REQUIRE(n_ids < 0x7FFFFFFFll, "hrb_embedding_bwd_dense_workspace: n_ids exceeds 2^31-1");
+  BwdWorkspace w;
+  int rc = carve_bwd_ws(n_ids > 0 ? n_ids : 1, 1, dim, 32, nullptr, w);
+  if (rc != HRB_OK) return rc;
+  *bytes = w.total + align_up(sizeof(TableDev));
+  return HRB_OK;
+}
+
+HRB_API int hrb_embedding_bwd_dense(const int32_t* ids, int64_t n_ids, const float* dout, int64_t vocab, int32_t dim,
+                                    const float* table, float l2_scale, float* dtable, void* workspace,
+                                    size_t workspace_bytes, void* stream) {
+  HRB_REQUIRE(ids && dout && dtable && workspace && n_ids >= 0 && vocab > 0 && dim > 0, "hrb_embedding_bwd_dense: null/negative argument");
+  if (dim % 4 != 0) return fail(HRB_UNSUPPORTED, "hrb_embedding_bwd_dense: dim %d is not a multiple of 4", dim);
+  HRB_REQUIRE(aligned16(dout) && aligned16(dtable), "hrb_embedding_bwd_dense: dout/dtable must be 16-byte aligned");
+  HRB_REQUIRE(vocab < 0xFFFFFFFFll && n_ids < 0x7FFFFFFFll, "hrb_embedding_bwd_dense: sizes exceed 32-bit keys");
+  cudaStream_t st = (cudaStream_t)stream;
+  dense_grad_init_kernel<<<grid_for(vocab * dim, 256), 256, 0, st>>>(l2_scale != 0.f ? table : nullptr, l2_scale,
+                                                                    vocab * (int64_t)dim, dtable);
+  HRB_LAUNCH_CHECK();
+  if (n_ids == 0) return HRB_OK;
+  const int key_bits = bits_for((uint64_t)vocab);
+  BwdWorkspace w;
+  int rc = carve_bwd_ws(n_ids, 1, dim, key_bits, workspace, w);
+  if (rc != HRB_OK) return rc;
+  const size_t need = w.total + align_up(sizeof(TableDev));
+  if (need > workspace_bytes)
+    return fail(HRB_WORKSPACE, "hrb_embedding_bwd_dense: workspace %zu < required %zu bytes", workspace_bytes, need);
+  TableDev* d_t = (TableDev*)((char*)workspace + w.total);
+  TableDev t{dtable, nullptr, nullptr, vocab, 0u, dim};
+  HRB_CUDA(cudaMemcpyAsync(d_t, &t, sizeof(t), cudaMemcpyHostToDevice, st));
+  const uint32_t sentinel = (uint32_t)vocab;
+  flat_keys_kernel<<<grid_for(n_ids, 256), 256, 0, st>>>(ids, n_ids, vocab, sentinel, w.keys_in, w.vals_in);
+  HRB_LAUNCH_CHECK();
+  FlatGrad src{dout, dim};
+  ApplyCtx ctx{d_t, 1, hrb_opt_params{}, dtable, 0.f};
+  return run_sorted_update(2, w, n_ids, sentinel, key_bits, dim / 4, src, ctx, st);
+}
+
+HRB_API int hrb_shard_ids(const hrb_plan* plan, const int32_t* ids, int64_t ids_ld, int64_t batch, int32_t n_ranks,
+                          int32_t* send, void* stream) {
+  HRB_REQUIRE(plan && ids && send && batch >= 0 && n_ranks > 0, "hrb_shard_ids: null/negative argument");
+  if (batch == 0) return HRB_OK;
+  shard_ids_kernel<<<grid_for(batch * plan->pos_cols, 256), 256, 0, (cudaStream_t)stream>>>(
+      plan->d_fields, plan->d_pos_field, plan->pos_cols, ids, ids_ld, batch, n_ranks, send);
+  HRB_LAUNCH_CHECK();
+  return HRB_OK;
+}
+
+HRB_API int hrb_lookup_partial_fwd(const hrb_plan* plan, const int32_t* local_ids, int64_t ids_ld, int64_t batch,
+                                   float* psum, int64_t out_ld, float* pcount, void* stream) {
+  int rc = check_lookup_args("hrb_lookup_partial_fwd", plan, local_ids, ids_ld, batch, psum, out_ld);
+  if (rc != HRB_OK) return rc;
+  HRB_REQUIRE(pcount != nullptr, "hrb_lookup_partial_fwd: pcount is NULL");
+  if (batch == 0) return HRB_OK;
+  const unsigned grid = grid_for(batch * plan->out_chunks, 256, 8);
+  lookup_items_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(plan->d_fields, plan->d_chunk_field,
+                                                                   plan->d_chunk_q, plan->out_chunks, plan->n_fields,
+                                                                   local_ids, ids_ld, batch, psum, out_ld, pcount,
+                                                                   nullptr);
+  HRB_LAUNCH_CHECK();
+  return HRB_OK;
+}
+
+HRB_API int hrb_lookup_combine(const hrb_plan* plan, const float* psum, const float* pcount, int32_t n_ranks,
+                               int64_t batch, int64_t out_ld, float* out, float* inv_count, void* stream) {
+  HRB_REQUIRE(plan && psum && pcount && out && n_ranks > 0 && batch >= 0, "hrb_lookup_combine: null/negative argument");
+  HRB_REQUIRE(aligned16(psum) && aligned16(out) && out_ld % 4 == 0, "hrb_lookup_combine: buffers must be 16-byte aligned");
+  if (batch == 0) return HRB_OK;
+  lookup_combine_kernel<<<grid_for(batch * plan->out_chunks, 256), 256, 0, (cudaStream_t)stream>>>(
+      plan->d_fields, plan->d_chunk_field, plan->d_chunk_q, plan->out_chunks, plan->n_fields, psum, pcount, n_ranks,
+      batch, out_ld, out, inv_count);
+  HRB_LAUNCH_CHECK();
+  return HRB_OK;
+}

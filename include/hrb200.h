@@ -1,0 +1,246 @@
+/*
+ * hrb200.h -- C ABI of libhrb200.so: the B200 (sm_100a) implementation of HandyRec's
+ * data-parallel hot path (embedding lookup + masked sequence pooling -> FM / DIN
+ * attention / dense towers, and the embedding backward).
+ *
+ * HandyRec (TF 2.6 / Keras, pure Python) has no FFI today; the path sits behind the
+ * Keras Layer protocol.  Each entry point below names the reference interface whose
+ * arithmetic it replaces (paths relative to /root/reference/).  The reference-side
+ * binding a maintainer would add (TF custom op / ctypes) is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - floats are fp32, ids are int32 (features/type.py:76,128), sizes are int64_t;
+ *   - the caller owns every buffer, including tables and workspaces; the library
+ *     allocates nothing except the small opaque hrb_plan (hrb_plan_create/destroy);
+ *   - every compute entry takes a cudaStream_t as `void* stream`, is asynchronous and
+ *     never synchronises the device; no internal streams;
+ *   - return value: 0 = HRB_OK, otherwise an hrb_status code; never throws or aborts.
+ *     hrb_last_error() returns a thread-local detail string.
+ */
+#ifndef HRB200_H_
+#define HRB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HRB_ABI_VERSION 1
+
+typedef enum hrb_status {
+  HRB_OK = 0,
+  HRB_BAD_ARG = 1,      /* null pointer, negative size, misaligned buffer ...            */
+  HRB_UNSUPPORTED = 2,  /* valid request the kernels do not cover (stated in the message) */
+  HRB_CUDA_ERROR = 3,   /* a CUDA runtime call failed (message holds cudaGetErrorString)  */
+  HRB_WORKSPACE = 4     /* workspace too small                                            */
+} hrb_status;
+
+/* pooling methods: layers/sequence.py:19-23 ("mean" | "max" | "sum"); NONE = plain lookup (L must be 1) */
+typedef enum hrb_pool { HRB_POOL_NONE = 0, HRB_POOL_MEAN = 1, HRB_POOL_SUM = 2, HRB_POOL_MAX = 3 } hrb_pool;
+
+/* activations: layers/utils.py:117-133 -> keras Activation(name); "dice" is its own entry point */
+typedef enum hrb_act {
+  HRB_ACT_LINEAR = 0,
+  HRB_ACT_RELU = 1,
+  HRB_ACT_SIGMOID = 2,
+  HRB_ACT_TANH = 3,
+  HRB_ACT_DICE = 4 /* only inside hrb_lau_fwd (inference statistics); standalone Dice is hrb_dice_fwd/bwd */
+} hrb_act;
+
+int hrb_abi_version(void);
+const char* hrb_status_str(int status);
+const char* hrb_last_error(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Synthetic tables.  table[r,c] = lo + u*(hi-lo), u = (hash(seed, (row_start+r*row_step)*dim+c)>>8)*2^-24.
+ * Bit-identical to oracle/layers_ref.py:hash_uniform_table.  Replaces Keras Embedding's
+ * `uniform` initialiser (features/group.py:285-293) for benchmarks and parity runs.
+ * ------------------------------------------------------------------------------------------ */
+int hrb_init_uniform(float* table, int64_t rows, int32_t dim, uint32_t seed, float lo, float hi,
+                     int64_t row_start, int64_t row_step, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * a5  CustomEmbedding.__call__ + compute_mask   (layers/tools.py:87-101)
+ *   out[i,:] = table[ids[i],:]  (row 0 is gathered like any row);
+ *   mask[i,d] = ids[i] != 0 tiled over dim (uint8 0/1), only when mask != NULL.
+ *   oob (nullable, int32[2], caller-zeroed): set to {1, first offending flat index seen} when an id
+ *   is outside [0,vocab); such rows are written as zeros (TF-GPU behaviour), TF-CPU raises.
+ * ------------------------------------------------------------------------------------------ */
+int hrb_embedding_fwd(const float* table, int64_t vocab, int32_t dim, const int32_t* ids, int64_t n_ids,
+                      float* out, uint8_t* mask, int32_t* oob, void* stream);
+
+/* Embedding backward as a DENSE table gradient (layer face; TF autodiff of a5):
+ *   dtable[r,:] = sum_{i: ids[i]==r} dout[i,:]   (+ l2_scale * table[r,:] when table != NULL)
+ * Sorted-segment reduction, no atomics, deterministic.  dtable (vocab x dim) is fully overwritten. */
+int hrb_embedding_bwd_dense_workspace(int64_t n_ids, int32_t dim, size_t* bytes);
+int hrb_embedding_bwd_dense(const int32_t* ids, int64_t n_ids, const float* dout, int64_t vocab, int32_t dim,
+                            const float* table, float l2_scale, float* dtable, void* workspace,
+                            size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * a6  SequencePoolingLayer.call   (layers/sequence.py:26-46)
+ *   x (B,L,D), mask (B,L,D) uint8 as produced by a5 -> out (B,1,D).  method: hrb_pool (not NONE).
+ *   mean: sum_l x*(mask/sum_l mask), divide_no_nan; sum: sum_l x*mask; max: max_l (x-(1-mask)*1e9).
+ *   bwd: dx (B,L,D) given dout (B,D); max distributes equally among ties (TF reduce_max gradient).
+ * ------------------------------------------------------------------------------------------ */
+int hrb_seq_pool_fwd(const float* x, const uint8_t* mask, int64_t batch, int32_t seq_len, int32_t dim,
+                     int32_t method, float* out, void* stream);
+int hrb_seq_pool_bwd(const float* x, const uint8_t* mask, const float* dout, int64_t batch, int32_t seq_len,
+                     int32_t dim, int32_t method, float* dx, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * a7  FeatureGroup.embedding_lookup   (features/group.py:299-336), fused: ids -> pooled (B, sum D)
+ *   A plan describes every sparse / sparse-sequence feature of a group: which table, where its ids
+ *   sit in the packed id matrix ids[B, ids_ld] (column ids_col .. ids_col+seq_len), the pooling
+ *   method, and the output column.  One launch does gather + mask + pool for all features; the
+ *   (B,L,D) tensor and its mask are never materialised.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct hrb_table_desc {
+  float* weight;  /* (rows, dim) fp32, 16-byte aligned                        */
+  float* adam_m;  /* optional first moment  (same shape) or NULL              */
+  float* adam_v;  /* optional second moment (same shape) or NULL              */
+  int64_t rows;   /* vocab_size                                               */
+  int32_t dim;    /* embedding dim                                            */
+  int32_t pad_;
+} hrb_table_desc;
+
+typedef struct hrb_field_desc {
+  int32_t table;    /* index into the plan's table array                                          */
+  int32_t seq_len;  /* 1 for SparseFeature; L for SparseSeqFeature                                */
+  int32_t pool;     /* hrb_pool; NONE => every id valid (mask_zero has no effect on the values)    */
+  int32_t ids_col;  /* first column of this feature in ids[B, ids_ld]                             */
+  int32_t out_col;  /* first output column (floats) in out[B, out_ld]                             */
+  int32_t pad_;
+} hrb_field_desc;
+
+typedef struct hrb_plan hrb_plan;
+
+int hrb_plan_create(const hrb_table_desc* tables_host, int32_t n_tables, const hrb_field_desc* fields_host,
+                    int32_t n_fields, hrb_plan** plan);
+int hrb_plan_destroy(hrb_plan* plan);
+
+/* fwd: out[b, out_col_f : +D_f] for every field.  inv_count (nullable): (B, n_fields) fp32, 1/n_valid
+ * (0 when none) for mean fields, 1 otherwise -- saved for the backward.  oob as in a5. */
+int hrb_lookup_fwd(const hrb_plan* plan, const int32_t* ids, int64_t ids_ld, int64_t batch, float* out,
+                   int64_t out_ld, float* inv_count, int32_t* oob, void* stream);
+
+/* fwd fused with a9 FM (layers/interaction.py:26-39) for the DeepFM case where the FM group and
+ * the DNN group hold the same features (models/ranking/context_aware/DeepFM.py:62-63): requires
+ * equal dims D and fields laid out contiguously (out_col_f = out_col_0 + f*D).
+ *   fm_out[b] = w0 + sum_f x_f . w + 0.5*sum_d[(sum_f x)^2 - sum_f x^2];  fm_sum[b,:] = sum_f x_f (for bwd) */
+int hrb_lookup_fm_fwd(const hrb_plan* plan, const int32_t* ids, int64_t ids_ld, int64_t batch, float* out,
+                      int64_t out_ld, float* inv_count, const float* fm_w, const float* fm_w0, float* fm_out,
+                      float* fm_sum, int32_t* oob, void* stream);
+
+/* a13 embedding backward + row update, fused plan face.
+ *   dout (B, dout_ld): gradient w.r.t. the pooled outputs (same column layout as out).
+ *   Sort (table,row) keys -> segment-reduce -> per-unique-row update, no atomics.
+ *   opt = HRB_OPT_SGD:       w[r] -= lr * (g[r] + l2_scale*w[r])        (touched rows only)
+ *   opt = HRB_OPT_ADAM_LAZY: Adam moments/weights updated for touched rows only (needs adam_m/adam_v)
+ *   max-pooled fields are not supported here (use a6 bwd + hrb_embedding_bwd_dense). */
+typedef enum hrb_opt { HRB_OPT_SGD = 0, HRB_OPT_ADAM_LAZY = 1 } hrb_opt;
+typedef struct hrb_opt_params {
+  int32_t opt;
+  float lr, beta1, beta2, eps, l2_scale; /* l2_scale = 2*l2_embd (features/group.py:289) */
+  float bias_corr1, bias_corr2;          /* 1-beta1^t, 1-beta2^t */
+} hrb_opt_params;
+int hrb_lookup_bwd_workspace(const hrb_plan* plan, int64_t ids_ld, int64_t batch, size_t* bytes);
+int hrb_lookup_bwd_update(const hrb_plan* plan, const int32_t* ids, int64_t ids_ld, int64_t batch,
+                          const float* dout, int64_t dout_ld, const float* inv_count,
+                          const hrb_opt_params* opt_host, void* workspace, size_t workspace_bytes,
+                          void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * a9  FM.call   (layers/interaction.py:15-39) on a materialised (B,F,D) tensor.
+ *   x rows are x_ld floats apart (x_ld >= F*D).  out (B).  fm_sum (nullable) (B,D).
+ *   bwd: dx[b,f,:] (+)= dout[b]*(w + S[b] - x[b,f,:]); dw[d] = sum_b dout[b]*S[b,d]; dw0 = sum_b dout[b].
+ *   dw_dw0: D+1 floats, overwritten.  accumulate!=0 adds into dx instead of overwriting.
+ * ------------------------------------------------------------------------------------------ */
+int hrb_fm_fwd(const float* x, int64_t x_ld, int64_t batch, int32_t fields, int32_t dim, const float* w,
+               const float* w0, float* out, float* fm_sum, void* stream);
+int hrb_fm_bwd(const float* x, int64_t x_ld, int64_t batch, int32_t fields, int32_t dim, const float* w,
+               const float* dout, float* dx, int64_t dx_ld, int32_t accumulate, float* dw_dw0, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * a11  Dense layers of DNN   (layers/core.py:53-78; Keras Dense = x@W+b)
+ *   fwd:   y[M,N] = act(x[M,K] @ w[K,N] + bias[N])
+ *   bwd_x: dx[M,K] = dz[M,N] @ w[K,N]^T, optionally * act'(a_prev) where a_prev[M,K] is the
+ *          previous layer's post-activation output (relu/sigmoid/tanh derivative from the output)
+ *   bwd_w: dw[K,N] = x[M,K]^T @ dz[M,N]; dbias[N] = sum_m dz[m,n]   (split over M, fixed-order reduce)
+ *   precision: fp32 FFMA (HRB_GEMM_FP32) or tcgen05 3xTF32 error-compensated (HRB_GEMM_3XTF32).
+ * ------------------------------------------------------------------------------------------ */
+typedef enum hrb_gemm_mode { HRB_GEMM_AUTO = 0, HRB_GEMM_FP32 = 1, HRB_GEMM_3XTF32 = 2 } hrb_gemm_mode;
+int hrb_dense_fwd(const float* x, int64_t ldx, const float* w, int64_t ldw, const float* bias, int64_t M,
+                  int32_t K, int32_t N, int32_t act, float* y, int64_t ldy, int32_t mode, void* stream);
+int hrb_dense_bwd_x(const float* dz, int64_t lddz, const float* w, int64_t ldw, int64_t M, int32_t K,
+                    int32_t N, const float* a_prev, int64_t lda_prev, int32_t act_prev, float* dx,
+                    int64_t lddx, int32_t mode, void* stream);
+int hrb_dense_bwd_w_workspace(int64_t M, int32_t K, int32_t N, size_t* bytes);
+int hrb_dense_bwd_w(const float* x, int64_t ldx, const float* dz, int64_t lddz, int64_t M, int32_t K,
+                    int32_t N, float* dw, int64_t lddw, float* dbias, void* workspace, size_t workspace_bytes,
+                    int32_t mode, void* stream);
+/* dz = dy * act'(y) in place-capable elementwise (used at the head of a backward chain) */
+int hrb_act_bwd(const float* y, const float* dy, int64_t n, int32_t act, float* dz, void* stream);
+
+/* Dice   (layers/activation.py:27-42): p = sigmoid((x-mean)*rsqrt(var+eps)); y = p*x + (1-p)*alpha*x.
+ * training != 0: mean/var are computed over all rows (biased) and written to batch_mean/batch_var;
+ * otherwise mean/var are read from them (moving statistics). */
+int hrb_dice_fwd(const float* x, int64_t rows, int32_t units, const float* alpha, float* mean, float* var,
+                 float eps, int32_t training, float* y, void* stream);
+int hrb_dice_bwd(const float* x, const float* dy, int64_t rows, int32_t units, const float* alpha,
+                 const float* mean, const float* var, float eps, int32_t training, float* dx, float* dalpha,
+                 float* scratch /* 2*units floats, training only */, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * a10  LocalActivationUnit.call + SqueezeMask + tf.matmul(att, keys)
+ *      (layers/sequence.py:92-102, layers/tools.py:104-113, models/ranking/sequential/DIN.py:87-93)
+ *   Fused per sample: att_in=[q,k,q-k,q*k] built on the fly (never materialised), MLP
+ *   [4D -> 4D -> h1 -> ... -> 1] with an elementwise activation (relu/sigmoid/tanh/linear, or dice in
+ *   inference mode via dice_* arrays), mask by ids != 0, no softmax; pooled[b,:] = sum_t score[b,t]*k[b,t,:].
+ *   The MLP is described by n_layers weight matrices packed back to back in `params`:
+ *   for layer i: W_i (in_i x out_i, row-major), b_i (out_i), then -- only when act == HRB_ACT_DICE and
+ *   i is not the last layer -- alpha_i, moving_mean_i, moving_var_i (out_i each); the running offset is
+ *   rounded up to a multiple of 4 floats after every layer.  in_0 = 4D; layer_out_host[0] is normally 4D
+ *   (core.py:57 prepends Dense(in)); the last layer must have 1 unit.
+ * ------------------------------------------------------------------------------------------ */
+int hrb_lau_fwd(const float* table, int64_t vocab, int32_t dim, const int32_t* query_ids,
+                const int32_t* key_ids, int64_t batch, int32_t seq_len, const float* params,
+                const int32_t* layer_out_host, int32_t n_layers, int32_t act, float* score, float* pooled,
+                void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * DeepFM head + loss   (models/ranking/context_aware/DeepFM.py:86-88 + Keras binary_crossentropy)
+ *   logit = dnn[b] + fm[b]; p = sigmoid(logit); loss_sum += bce(logit,y); dlogit[b] = (p-y)*grad_scale
+ *   loss_sum: one float, caller-zeroed, accumulated with a fixed-order block reduction + one atomic per block.
+ * ------------------------------------------------------------------------------------------ */
+int hrb_sigmoid_bce(const float* dnn_logit, const float* fm_logit, const float* label, int64_t batch,
+                    float grad_scale, float* prob, float* dlogit, float* loss_sum, void* stream);
+
+/* Dense-parameter optimisers on a flat fp32 buffer (Keras Adam / SGD formulas). */
+int hrb_adam_step(float* param, const float* grad, float* m, float* v, int64_t n, float lr, float beta1,
+                  float beta2, float eps, float bias_corr1, float bias_corr2, float l2_scale, void* stream);
+int hrb_sgd_step(float* param, const float* grad, int64_t n, float lr, float l2_scale, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * (e) row-sharded tables: owner(r) = r % n_ranks, local row r / n_ranks  (SURVEY §8e).
+ *   bucketize: for ids[B, ids_ld] write, per destination rank, the LOCAL row of every id that rank
+ *   owns and 0xFFFFFFFF (= "not yours") elsewhere -- a dense (n_ranks, B, ids_ld) int32 tensor ready for
+ *   a fixed-size all-to-all; padding ids (0 in a pooled field) are sent as "not yours".
+ * ------------------------------------------------------------------------------------------ */
+int hrb_shard_ids(const hrb_plan* plan, const int32_t* ids, int64_t ids_ld, int64_t batch, int32_t n_ranks,
+                  int32_t* send, void* stream);
+/* owner side: partial pooling of the rows this rank owns: psum[b, out cols] and pcount[b, field]
+ * for `batch` = (requesting ranks * their batch) rows of remote ids. */
+int hrb_lookup_partial_fwd(const hrb_plan* plan, const int32_t* local_ids, int64_t ids_ld, int64_t batch,
+                           float* psum, int64_t out_ld, float* pcount, void* stream);
+/* requester side: out = finalise(sum_r psum[r], sum_r pcount[r]) */
+int hrb_lookup_combine(const hrb_plan* plan, const float* psum, const float* pcount, int32_t n_ranks,
+                       int64_t batch, int64_t out_ld, float* out, float* inv_count, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HRB200_H_ */

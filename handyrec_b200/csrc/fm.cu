@@ -21,18 +21,25 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
-      "WAIT_LOOP:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra DONE;\n"
-      "bra WAIT_LOOP;\n"
-      "DONE:\n"
-      "}\n" ::"r"(smem_u32(bar)),
-      "r"(parity)
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
       : "memory");
+  return ok != 0;
+}
+// bounded wait: a lost transaction becomes a trap (-> CUDA error), never a hung GPU
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity))
+    if (clock64() - t0 > 4000000000LL) __trap();  // ~2 s
 }
 __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
@@ -67,43 +74,45 @@ __global__ void __launch_bounds__(256) fm_fwd_tma_kernel(const float* __restrict
   }
   __syncthreads();
 
-  auto issue = [&](int64_t tile, int st) {  // executed by warp 0
+  auto issue = [&](int64_t tile, int st) {  // executed by thread 0 only
     const int64_t b0 = tile * TS;
     const int rows = (int)min((int64_t)TS, batch - b0);
-    if (threadIdx.x == 0) mbar_expect_tx(&full[st], row_bytes * (uint32_t)rows);
-    __syncwarp();
-    for (int r = threadIdx.x; r < rows; r += 32)
+    mbar_expect_tx(&full[st], row_bytes * (uint32_t)rows);
+    for (int r = 0; r < rows; ++r)
       bulk_g2s(stage[st] + (size_t)r * pitch, x + (b0 + r) * x_ld, row_bytes, &full[st]);
   };
 
   const float4 w4 = __ldg(reinterpret_cast<const float4*>(w) + q);
   const float bias = __ldg(w0);
   int64_t tile = blockIdx.x;
-  if (tile < n_tiles && threadIdx.x < 32) issue(tile, 0);
+  if (tile < n_tiles && threadIdx.x == 0) issue(tile, 0);
   uint32_t phase[2] = {0, 0};
   int st = 0;
   for (; tile < n_tiles; tile += gridDim.x, st ^= 1) {
     const int64_t next = tile + gridDim.x;
-    if (next < n_tiles && threadIdx.x < 32) issue(next, st ^ 1);  // stage st^1 was drained one iteration ago
+    if (next < n_tiles && threadIdx.x == 0) issue(next, st ^ 1);  // stage st^1 was drained one iteration ago
     mbar_wait(&full[st], phase[st]);
     phase[st] ^= 1;
     const int64_t b = tile * TS + s;
-    if (b < batch) {
+    const bool valid = b < batch;  // lanes past the end still take part in the shuffles below
+    float4 S = make_float4(0.f, 0.f, 0.f, 0.f), Q = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (valid) {
       const float4* row = reinterpret_cast<const float4*>(stage[st] + (size_t)s * pitch) + q;
-      float4 S = make_float4(0.f, 0.f, 0.f, 0.f), Q = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 4
       for (int f = 0; f < F; ++f) {
         const float4 v = row[f * G];
         S.x += v.x; S.y += v.y; S.z += v.z; S.w += v.w;
         Q.x = fmaf(v.x, v.x, Q.x); Q.y = fmaf(v.y, v.y, Q.y); Q.z = fmaf(v.z, v.z, Q.z); Q.w = fmaf(v.w, v.w, Q.w);
       }
-      float p2 = S.x * w4.x + S.y * w4.y + S.z * w4.z + S.w * w4.w;
-      float p3 = (S.x * S.x - Q.x) + (S.y * S.y - Q.y) + (S.z * S.z - Q.z) + (S.w * S.w - Q.w);
+    }
+    float p2 = S.x * w4.x + S.y * w4.y + S.z * w4.z + S.w * w4.w;
+    float p3 = (S.x * S.x - Q.x) + (S.y * S.y - Q.y) + (S.z * S.z - Q.z) + (S.w * S.w - Q.w);
 #pragma unroll
-      for (int o = G / 2; o > 0; o >>= 1) {
-        p2 += __shfl_xor_sync(0xffffffffu, p2, o, G);
-        p3 += __shfl_xor_sync(0xffffffffu, p3, o, G);
-      }
+    for (int o = G / 2; o > 0; o >>= 1) {
+      p2 += __shfl_xor_sync(0xffffffffu, p2, o, G);
+      p3 += __shfl_xor_sync(0xffffffffu, p3, o, G);
+    }
+    if (valid) {
       if (q == 0) out[b] = p2 + 0.5f * p3 + bias;
       if (fm_sum != nullptr) reinterpret_cast<float4*>(fm_sum + b * D)[q] = S;
     }

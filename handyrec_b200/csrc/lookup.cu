@@ -335,9 +335,13 @@ __global__ void __launch_bounds__(256) lookup_rows_kernel(const FieldDev* __rest
     w4 = __ldg(reinterpret_cast<const float4*>(fm_w) + q);
     w0 = __ldg(fm_w0);
   }
-  for (int64_t b = blockIdx.x * (int64_t)SPB + s_in_block; b < batch; b += (int64_t)gridDim.x * SPB) {
-    const int32_t* ids_row = ids + b * ids_ld;
-    float* out_row = out + b * out_ld;
+  // the loop bound is block-uniform; lanes past the end stay in it (valid == false) because the FM
+  // epilogue shuffles with a full mask
+  for (int64_t b0 = blockIdx.x * (int64_t)SPB; b0 < batch; b0 += (int64_t)gridDim.x * SPB) {
+    const int64_t b = b0 + s_in_block;
+    const bool valid = b < batch;
+    const int32_t* ids_row = ids + (valid ? b : 0) * ids_ld;
+    float* out_row = out + (valid ? b : 0) * out_ld;
     float4 S = make_float4(0.f, 0.f, 0.f, 0.f);
     float4 Q = make_float4(0.f, 0.f, 0.f, 0.f);
     if (LEN1) {
@@ -346,11 +350,11 @@ __global__ void __launch_bounds__(256) lookup_rows_kernel(const FieldDev* __rest
         int32_t id[FU];
         float4 v[FU];
 #pragma unroll
-        for (int u = 0; u < FU; ++u) id[u] = (f0 + u < n_fields) ? __ldg(ids_row + fields[f0 + u].ids_col) : 0;
+        for (int u = 0; u < FU; ++u) id[u] = (valid && f0 + u < n_fields) ? __ldg(ids_row + fields[f0 + u].ids_col) : 0;
 #pragma unroll
         for (int u = 0; u < FU; ++u) {
           v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (f0 + u < n_fields) {
+          if (valid && f0 + u < n_fields) {
             const FieldDev& f = fields[f0 + u];
             if (id[u] >= 0 && (int64_t)id[u] < f.rows) {
               v[u] = ldg_nc_na(reinterpret_cast<const float4*>(f.table) + (int64_t)id[u] * G + q);
@@ -362,7 +366,7 @@ __global__ void __launch_bounds__(256) lookup_rows_kernel(const FieldDev* __rest
         }
 #pragma unroll
         for (int u = 0; u < FU; ++u) {
-          if (f0 + u < n_fields) {
+          if (valid && f0 + u < n_fields) {
             stg_na(reinterpret_cast<float4*>(out_row + fields[f0 + u].out_col) + q, v[u]);
             if (FM) {
               S.x += v[u].x; S.y += v[u].y; S.z += v[u].z; S.w += v[u].w;
@@ -372,10 +376,10 @@ __global__ void __launch_bounds__(256) lookup_rows_kernel(const FieldDev* __rest
           }
         }
       }
-      if (inv_count != nullptr)
+      if (inv_count != nullptr && valid)
         for (int f = q; f < n_fields; f += G) inv_count[b * n_fields + f] = 1.0f;
     } else {
-      for (int fi = 0; fi < n_fields; ++fi) {
+      for (int fi = 0; valid && fi < n_fields; ++fi) {
         const FieldDev f = fields[fi];
         float n_valid;
         const float4 r = pooled_chunk<false>(f, ids_row, q, n_valid, oob, b);
@@ -399,8 +403,8 @@ __global__ void __launch_bounds__(256) lookup_rows_kernel(const FieldDev* __rest
         p2 += __shfl_xor_sync(0xffffffffu, p2, o, G);
         p3 += __shfl_xor_sync(0xffffffffu, p3, o, G);
       }
-      if (q == 0) fm_out[b] = p2 + 0.5f * p3 + w0;
-      if (fm_sum != nullptr) reinterpret_cast<float4*>(fm_sum + b * (int64_t)(G * 4))[q] = S;
+      if (valid && q == 0) fm_out[b] = p2 + 0.5f * p3 + w0;
+      if (valid && fm_sum != nullptr) reinterpret_cast<float4*>(fm_sum + b * (int64_t)(G * 4))[q] = S;
     }
   }
 }
@@ -787,7 +791,9 @@ using namespace hrb;
 // =============================================================================================
 HRB_API int hrb_embedding_fwd(const float* table, int64_t vocab, int32_t dim, const int32_t* ids, int64_t n_ids,
                               float* out, uint8_t* mask, int32_t* oob, void* stream) {
-  HRB_REQUIRE(table && ids && out && vocab > 0 && dim > 0 && n_ids >= 0, "hrb_embedding_fwd: null/negative argument");
+  HRB_REQUIRE(vocab > 0 && dim > 0 && n_ids >= 0, "hrb_embedding_fwd: null/negative argument");
+  if (n_ids == 0) return HRB_OK;  // empty batch: nothing to read or write (pointers may be NULL)
+  HRB_REQUIRE(table && ids && out, "hrb_embedding_fwd: null/negative argument");
   if (dim % 4 != 0) return fail(HRB_UNSUPPORTED, "hrb_embedding_fwd: dim %d is not a multiple of 4", dim);
   HRB_REQUIRE(aligned16(table) && aligned16(out), "hrb_embedding_fwd: table/out must be 16-byte aligned");
   HRB_REQUIRE(mask == nullptr || (reinterpret_cast<uintptr_t>(mask) & 3u) == 0, "hrb_embedding_fwd: mask must be 4-byte aligned");

@@ -1,0 +1,334 @@
+#!/usr/bin/env python
+"""bench.py -- DeepFM train samples/s on synthetic Criteo-shape data (BASELINE.json configs[2]).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --steps K --warmup W    # the reference restated on CPU (oracle)
+
+One "step" = one full DeepFM training step (lookup+pool, FM, DNN forward, BCE, backward, sorted-segment
+embedding update, dense optimiser) on one batch of 65536 synthetic samples (26 sparse + 13 dense, D=16).
+Prints ONE JSON line (contract in the task statement): `value` = device-resident throughput, `e2e` =
+through the host-facing API with pinned host buffers (H2D + D2H inside the timed region), `roofline` for the
+dominant kernel, `roofline_lookup` for the embedding lookup (the north-star kernel), `cpu_baseline`.
+Nothing here reads /root/reference.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+# Criteo-like vocabulary vector, +1 so that id 0 exists everywhere
+CRITEO_VOCABS = [40_000_000, 40_000_000, 10_000_000, 5_000_000, 3_000_000, 2_000_000, 1_000_000, 500_000, 300_000, 100_000,
+                 50_000, 20_000, 12_000, 10_000, 7_000, 5_000, 2_000, 1_500, 1_000, 600, 300, 100, 30, 20, 10, 4]
+CRITEO_VOCABS = [v + 1 for v in CRITEO_VOCABS]
+N_DENSE, EMB_DIM, BATCH = 13, 16, 65536
+DNN_HIDDEN = (256, 128, 1)
+LOOKUP_BYTES_PER_SAMPLE = len(CRITEO_VOCABS) * (4 + EMB_DIM * 4 + EMB_DIM * 4)  # ids + rows + output = 3432
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": float(d["hbm_gbs"]), "bf16_tflops": float(d["bf16_tflops"]), "bf16_tflops_sustained": float(d.get("bf16_tflops_sustained", d["bf16_tflops"])), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=lambda: [self.lines.append(l) for l in self.proc.stdout], daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# -------------------------------------------------------------------------------------------------
+# CPU restatement of one training step (oracle) -- used by cpu_baseline and by --impl reference
+# -------------------------------------------------------------------------------------------------
+def cpu_reference_arm(batch: int, vocab_cap: int, steps: int, warmup: int, seed: int = 1234):
+    """Time the op-for-op CPU restatement (oracle/) of the same DeepFM step on a bounded sample.
+
+    Same model (26 tables D=16, 13 dense, DNN [429,256,128,1], FM, BCE, Adam), embeddings looked up once
+    per feature group exactly like the reference (DeepFM.py:62-63), dense-table gradients + dense Adam like
+    Keras.  Vocabularies are capped at `vocab_cap` rows so that the dense Adam state fits and a step stays bounded.
+    """
+    import torch
+
+    import oracle
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    g = torch.Generator().manual_seed(seed)
+    vocabs = [min(v, vocab_cap) for v in CRITEO_VOCABS]
+    tables = [((torch.rand(v, EMB_DIM, generator=g) - 0.5) * 0.1).requires_grad_(True) for v in vocabs]
+    p = oracle.dnn_init(N_DENSE + len(vocabs) * EMB_DIM, DNN_HIDDEN, seed=seed)
+    for t in p.W + p.b:
+        t.requires_grad_(True)
+    fm_w = (torch.rand(EMB_DIM, 1, generator=g) - 0.5).requires_grad_(True)
+    fm_w0 = torch.zeros(1, requires_grad=True)
+    params = tables + p.W + p.b + [fm_w, fm_w0]
+    opt = torch.optim.Adam(params, lr=1e-3, eps=1e-7)
+    ids = torch.stack([torch.randint(0, v, (batch,), generator=g) for v in vocabs], 1)
+    dense = torch.log1p(torch.empty(batch, N_DENSE).exponential_(1.0, generator=g))
+    label = (torch.rand(batch, generator=g) < 0.25).float()
+    from collections import OrderedDict
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        sparse = OrderedDict((f"C{f}", (tables[f], ids[:, f : f + 1], False)) for f in range(len(vocabs)))
+        fm_embds = oracle.group_embedding_lookup(sparse, OrderedDict(), "mean")   # fm_feature_group.embedding_lookup
+        dnn_embds = oracle.group_embedding_lookup(sparse, OrderedDict(), "mean")  # dnn_feature_group.embedding_lookup
+        logit = oracle.deepfm_forward([dense], fm_embds, dnn_embds, p, fm_w, fm_w0, return_logit=True)
+        loss = oracle.bce_from_logits(logit[:, 0], label)
+        loss.backward()
+        opt.step()
+        return float(loss.detach())
+
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    return {"samples_per_s": batch * steps / dt, "ms_per_step": dt / steps * 1e3, "cores": torch.get_num_threads(),
+            "sample": f"{steps} steps of batch {batch}, vocab capped at {vocab_cap} rows/table, Adam, torch-CPU op-for-op restatement (TF unavailable in image)"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    r = cpu_reference_arm(batch=8192, vocab_cap=200_000, steps=args.steps, warmup=args.warmup)
+    line = {
+        "impl": "reference", "metric": "DeepFM train samples/s", "value": r["samples_per_s"], "unit": "samples/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "DeepFM Criteo-shape (26 sparse + 13 dense, D=16, DNN 429-256-128-1), CPU restatement of the reference", "global_batch": 8192},
+        "cpu_baseline": {"value": r["samples_per_s"], "unit": "samples/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]},
+        "e2e": {"value": r["samples_per_s"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# -------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--optimizer", default="adam", choices=["adam", "sgd"])
+    ap.add_argument("--ids", default="uniform", choices=["uniform", "zipf"])
+    ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--scale-vocab", type=float, default=1.0, help="shrink every vocabulary (debug only; reported in config)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+
+    from handyrec_b200 import _lib
+    from handyrec_b200 import kernels as K
+    from handyrec_b200.engine import DeepFMEngine, launch_count
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=dev)
+    peaks = load_peaks()
+
+    # ---- workload -------------------------------------------------------------------------------
+    B = args.batch
+    vocabs = [max(4, int(v * args.scale_vocab)) for v in CRITEO_VOCABS]
+    tables = []
+    for f, v in enumerate(vocabs):
+        t = torch.empty(v, EMB_DIM, device=dev)
+        K.init_uniform(t, seed=7 + f)
+        tables.append(t)
+    fields = [(f, 1, "none") for f in range(len(vocabs))]
+    eng = DeepFMEngine(tables, fields, N_DENSE, DNN_HIDDEN, "relu", batch_size=B, optimizer=args.optimizer, lr=1e-3, l2_embd=0.0, seed=2022)
+    NB = 4  # rotating pool of distinct batches (tables are 6.5 GB >> 126 MB L2: every step touches fresh rows)
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    ids_pool, dense_pool, label_pool = [], [], []
+    for _ in range(NB):
+        cols = []
+        for v in vocabs:
+            if args.ids == "uniform":
+                cols.append(torch.randint(0, v, (B,), device=dev, generator=g, dtype=torch.int64))
+            else:  # Zipf(1.05) over [1, V): inverse-CDF of the continuous approximation
+                u = torch.rand(B, device=dev, generator=g, dtype=torch.float64)
+                a = 1.05
+                x = ((v ** (1 - a) - 1) * u + 1) ** (1 / (1 - a))
+                cols.append(x.long().clamp_(1, v - 1))
+        ids_pool.append(torch.stack(cols, 1).to(torch.int32).contiguous())
+        dense_pool.append(torch.log1p(torch.empty(B, N_DENSE, device=dev).exponential_(1.0, generator=g)))
+        label_pool.append((torch.rand(B, device=dev, generator=g) < 0.25).float())
+    host = [(i.cpu().pin_memory(), d.cpu().pin_memory(), l.cpu().pin_memory()) for i, d, l in zip(ids_pool, dense_pool, label_pool)]
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timed region -----------------------------------------------------------
+    for s in range(args.warmup):
+        eng.train_step_on_device(ids_pool[s % NB], dense_pool[s % NB], label_pool[s % NB])
+    barrier()
+    l0 = launch_count()
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for s in range(args.steps):
+        eng.train_step_on_device(ids_pool[s % NB], dense_pool[s % NB], label_pool[s % NB])
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = launch_count() - l0
+
+    # ---- end-to-end through the host-facing API (pinned host buffers, H2D + D2H inside) ----------
+    for s in range(2):
+        eng.train_on_batch(*host[s % NB])
+    barrier()
+    t0 = time.perf_counter()
+    loss = 0.0
+    for s in range(args.steps):
+        loss = eng.train_on_batch(*host[s % NB])
+    torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - t0) * 1e3
+    clk = clocks.stop()
+
+    if world > 1:
+        import torch.distributed as dist
+
+        t = torch.tensor([ms, e2e_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, e2e_ms = float(t[0]), float(t[1])
+
+    # ---- per-kernel timing (CUDA events on the launching stream, same steps) ----------------------
+    phases = {}
+    reps = max(5, min(args.steps, 20))
+    for s in range(reps):
+        for k, v in eng.profile_step(ids_pool[s % NB], dense_pool[s % NB], label_pool[s % NB]).items():
+            phases[k] = phases.get(k, 0.0) + v / reps
+    # lookup kernel alone, back to back (burst), for the roofline of the north-star kernel
+    barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for s in range(reps):
+        eng.plan.forward(ids_pool[s % NB], out=eng.X0, fm=(eng.fm_w, eng.fm_w0), want_fm_sum=False)
+    b.record()
+    torch.cuda.synchronize()
+    lookup_alone_ms = a.elapsed_time(b) / reps
+
+    if rank != 0:
+        return
+    step_ms = ms / args.steps
+    total_phase = sum(phases.values())
+    dom = max(phases, key=phases.get)
+    flops = {}
+    units = eng.units
+    Ks = [eng.K0] + units[:-1]
+    for i, (kk, n) in enumerate(zip(Ks, units)):
+        f = 2.0 * B * kk * n
+        flops[f"dense_fwd_{i}"] = f
+        flops[f"dense_bwd_w_{i}"] = f
+        flops[f"dense_bwd_x_{i}"] = f
+    lookup_bytes = LOOKUP_BYTES_PER_SAMPLE * B
+
+    def roofline_for(name, dur_ms, peak_kind):
+        if name in flops:
+            ach = flops[name] / (dur_ms * 1e-3) / 1e12
+            peak = peaks["bf16_tflops_sustained"]
+            return {"kernel": name, "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+                    "peak_source": f"{peaks['source']} bf16 sustained; fp32-parity path, see DESIGN.md"}
+        ach = lookup_bytes / (dur_ms * 1e-3) / 1e9
+        peak = peaks["hbm_gbs"]
+        return {"kernel": name, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                "peak_source": f"{peaks['source']} copy bandwidth ({peak_kind})"}
+
+    roofline = roofline_for(dom, phases[dom], "sustained") if dom in flops or dom == "lookup_fm_fwd" else {
+        "kernel": dom, "bound": "hbm", "achieved": None, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": None, "traffic": None}
+    roofline["share_of_step"] = phases[dom] / total_phase
+    rl_lookup = roofline_for("lookup_fm_fwd", phases["lookup_fm_fwd"], "in-step")
+    rl_lookup["alone_ms"] = lookup_alone_ms
+    rl_lookup["alone_achieved"] = lookup_bytes / (lookup_alone_ms * 1e-3) / 1e9
+    rl_lookup["alone_frac"] = rl_lookup["alone_achieved"] / peaks["hbm_gbs"]
+    rl_lookup["bytes_per_sample"] = LOOKUP_BYTES_PER_SAMPLE
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        r = cpu_reference_arm(batch=8192, vocab_cap=200_000, steps=3, warmup=1)
+        cpu = {"value": r["samples_per_s"], "unit": "samples/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]}
+
+    line = {
+        "metric": "DeepFM train samples/s", "value": B * world * args.steps / (ms * 1e-3), "unit": "samples/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "DeepFM Criteo-shape: 26 sparse + 13 dense, emb dim 16, DNN 429-256-128-1, batch 65536/GPU (BASELINE.json configs[2])",
+                   "global_batch": B * world, "tables_rows": sum(vocabs), "tables_gb": sum(vocabs) * EMB_DIM * 4 / 1e9, "ids": args.ids,
+                   "optimizer": f"{args.optimizer} (dense params) + {eng.emb_opt} (touched embedding rows)", "l2_embd": 0.0,
+                   "l2_flush": "inputs larger than L2 (6.5 GB of tables, rotating pool of 4 batches)", "scale_vocab": args.scale_vocab},
+        "e2e": {"value": B * world * args.steps / (e2e_ms * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": eng.h2d_bytes_per_step(B), "d2h_bytes_per_step": 4,
+                "ms_per_step": e2e_ms / args.steps, "last_loss": loss},
+        "gpu_launches": launches, "gpu_launches_per_step": launches / max(args.steps, 1),
+        "clocks": clk, "roofline": roofline, "roofline_lookup": rl_lookup, "cpu_baseline": cpu,
+        "kernel_ms": {k: round(v, 4) for k, v in phases.items()},
+    }
+    print(json.dumps(line), flush=True)
+
+
+if __name__ == "__main__":
+    main()

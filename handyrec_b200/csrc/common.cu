@@ -1,6 +1,8 @@
 // common.cu -- status strings, thread-local error detail, device attribute cache, table init.
 #include <stdarg.h>
 
+#include <atomic>
+
 #include "common.cuh"
 
 namespace hrb {
@@ -16,6 +18,10 @@ int fail(int status, const char* fmt, ...) {
   va_end(ap);
   return status;
 }
+
+static std::atomic<long long> g_launches{0};
+void count_launches(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+long long launches() { return g_launches.load(std::memory_order_relaxed); }
 
 int sm_count() {
   static int cached[64] = {0};
@@ -59,6 +65,13 @@ HRB_API const char* hrb_status_str(int status) {
 }
 
 HRB_API const char* hrb_last_error(void) { return hrb::err_buf(); }
+
+namespace hrb { long long launches(); }
+HRB_API int hrb_launch_count(int64_t* count) {
+  HRB_REQUIRE(count != nullptr, "hrb_launch_count: count is NULL");
+  *count = (int64_t)hrb::launches();
+  return HRB_OK;
+}
 
 HRB_API int hrb_init_uniform(float* table, int64_t rows, int32_t dim, uint32_t seed, float lo, float hi,
                              int64_t row_start, int64_t row_step, void* stream) {

@@ -28,10 +28,17 @@ int fail(int status, const char* fmt, ...);
                          cudaGetErrorString(e_));                                               \
   } while (0)
 
-#define HRB_LAUNCH_CHECK() HRB_CUDA(cudaGetLastError())
+// every kernel launch of this library goes through this macro: it counts the launch
+// (hrb_launch_count) and surfaces launch-configuration errors
+#define HRB_LAUNCH_CHECK()             \
+  do {                                 \
+    ::hrb::count_launches(1);          \
+    HRB_CUDA(cudaGetLastError());      \
+  } while (0)
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
+void count_launches(int n);
 int sm_count();  // cached cudaDevAttrMultiProcessorCount of the current device
 
 // ---------------------------------------------------------------------------------------------

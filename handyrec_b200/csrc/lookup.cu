@@ -759,6 +759,7 @@ static int run_sorted_update(int mode, const BwdWorkspace& w, int64_t n, uint32_
   size_t cub_bytes = w.cub_bytes;
   HRB_CUDA(cub::DeviceRadixSort::SortPairs(w.cub_tmp, cub_bytes, w.keys_in, w.keys_out, w.vals_in, w.vals_out,
                                            (int)n, 0, key_bits, st));
+  count_launches(1 + (key_bits + 7) / 8);  // CUB onesweep: one histogram pass + one pass per 8 key bits
   const int64_t n_chunks = (n + CH - 1) / CH;
   const int threads = 256;
   const int gpb = threads / G;

@@ -160,6 +160,18 @@ __global__ void __launch_bounds__(256) dice_bwd_kernel(const float* __restrict__
   }
 }
 
+// dense features -> the head columns of the DNN input row (layers/utils.py:28-36 casts ints to fp32)
+template <typename T>
+__global__ void __launch_bounds__(256) pack_dense_kernel(const T* __restrict__ src, int64_t src_ld, int64_t batch,
+                                                        int32_t n, int32_t n_pad, float* __restrict__ dst, int64_t dst_ld) {
+  const int64_t total = batch * n_pad;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = i / n_pad;
+    const int c = (int)(i - b * n_pad);
+    dst[b * dst_ld + c] = c < n ? (float)src[b * src_ld + c] : 0.0f;
+  }
+}
+
 static inline unsigned ew_grid(int64_t n) {
   int64_t b = (n + 255) / 256;
   const int64_t cap = (int64_t)sm_count() * 8;
@@ -222,6 +234,7 @@ HRB_API int hrb_dice_fwd(const float* x, int64_t rows, int32_t units, const floa
     scale_kernel<<<(units + 255) / 256, 256, 0, st>>>(mean, units, 1.0f / (float)rows);
     dice_colstat_kernel<1><<<grid, 256, 0, st>>>(x, nullptr, rows, units, rpb, nullptr, mean, nullptr, eps, var, nullptr);
     scale_kernel<<<(units + 255) / 256, 256, 0, st>>>(var, units, 1.0f / (float)rows);
+    hrb::count_launches(3);
     HRB_LAUNCH_CHECK();
   }
   dice_apply_kernel<<<ew_grid(rows * units), 256, 0, st>>>(x, rows * units, units, alpha, mean, var, eps, y);
@@ -246,6 +259,19 @@ HRB_API int hrb_dice_bwd(const float* x, const float* dy, int64_t rows, int32_t 
     HRB_LAUNCH_CHECK();
   }
   dice_bwd_kernel<<<grid, 256, 0, st>>>(x, dy, rows, units, rpb, alpha, mean, var, eps, training, scratch, dx, dalpha);
+  HRB_LAUNCH_CHECK();
+  return HRB_OK;
+}
+
+HRB_API int hrb_pack_dense(const void* src, int32_t src_is_int32, int64_t src_ld, int64_t batch, int32_t n, int32_t n_pad,
+                           float* dst, int64_t dst_ld, void* stream) {
+  HRB_REQUIRE(batch >= 0 && n >= 0 && n_pad >= n && src_ld >= n && dst_ld >= n_pad, "hrb_pack_dense: bad sizes");
+  if (batch == 0 || n_pad == 0) return HRB_OK;
+  HRB_REQUIRE(src && dst, "hrb_pack_dense: null pointer");
+  if (src_is_int32)
+    pack_dense_kernel<int32_t><<<ew_grid(batch * n_pad), 256, 0, (cudaStream_t)stream>>>((const int32_t*)src, src_ld, batch, n, n_pad, dst, dst_ld);
+  else
+    pack_dense_kernel<float><<<ew_grid(batch * n_pad), 256, 0, (cudaStream_t)stream>>>((const float*)src, src_ld, batch, n, n_pad, dst, dst_ld);
   HRB_LAUNCH_CHECK();
   return HRB_OK;
 }

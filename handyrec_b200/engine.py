@@ -1,0 +1,337 @@
+"""Fused DeepFM training / inference engine on top of the C ABI.
+
+This is the execution plan that ``handyrec_b200.models.DeepFM`` runs when the FM group and the
+DNN group hold the same features (the reference's shipped configs, e.g.
+/root/reference/tests/ml-1m-test/DeepFM_cfg.yaml and examples/DeepFM/DeepFM_cfg.yaml): every
+table is looked up ONCE (the reference does it twice, DeepFM.py:62-63), the pooled (B, F, D) block
+is written once and serves as FM input and as the tail of the DNN input row, and the embedding
+gradient of both paths meets in one sorted-segment update.
+
+Data layout of one batch in HBM (all fp32, row-major):
+  X0   (B, K0p)   [dense (n_dense) | zero pad to a multiple of 4 | F pooled embeddings of D floats]
+  A_i  (B, ld_i)  activations of Dense layer i (ld_i = round-up-4(units_i))
+  params          ONE flat buffer: W_0 | b_0 | ... | W_n | b_n | fm_w (D) | fm_w0 (1), every block padded
+                  to 4 floats; W_i is (K_i_padded, ld_i) with zero rows/columns at the padding
+  grads / adam m,v  same layout as params
+Reference order of the DNN input is kept (dense first, layers/utils.py:70-84); the padding rows of
+W_0 multiply zero columns of X0 and receive zero gradients, so they stay zero.
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from . import kernels as K
+from ._lib import call
+
+
+def _r4(n: int) -> int:
+    return (n + 3) // 4 * 4
+
+
+def launch_count() -> int:
+    c = ctypes.c_int64(0)
+    call("hrb_launch_count", ctypes.byref(c))
+    return c.value
+
+
+class DeepFMEngine:
+    """DeepFM (models/ranking/context_aware/DeepFM.py) with shared FM / DNN feature groups.
+
+    fields: list of (table_index, seq_len, pool) in reference order (sparse features first, then
+    sequence features, features/group.py:319-334); all tables must share one embedding dim.
+    """
+
+    def __init__(
+        self,
+        tables: Sequence[torch.Tensor],
+        fields: Sequence[Tuple[int, int, str]],
+        n_dense: int,
+        dnn_hidden_units: Sequence[int] = (64, 32, 1),
+        dnn_activation: str = "relu",
+        batch_size: int = 4096,
+        optimizer: str = "adam",
+        lr: float = 1e-3,
+        l2_embd: float = 0.0,
+        l2_dnn: float = 0.0,
+        embedding_optimizer: Optional[str] = None,
+        seed: int = 2022,
+        gemm_mode: int = _lib.GEMM_AUTO,
+        task: str = "binary",
+    ):
+        if dnn_hidden_units[-1] != 1:  # DeepFM.py:59-60
+            raise ValueError("Output size of dnn should be 1")
+        if dnn_activation not in ("relu", "sigmoid", "tanh", "linear", None):
+            raise ValueError(f"fused engine supports relu/sigmoid/tanh/linear DNN activations, got {dnn_activation!r}")
+        if task != "binary":
+            raise ValueError("fused engine implements task='binary'")
+        self.dev = tables[0].device
+        self.tables = list(tables)
+        self.D = int(tables[0].shape[1])
+        if any(int(t.shape[1]) != self.D for t in tables):
+            raise ValueError("FM needs one embedding dim for every field (Concatenate(axis=1), layers/utils.py:40)")
+        self.F = len(fields)
+        self.n_dense = int(n_dense)
+        self.nd_pad = _r4(self.n_dense)
+        self.B = int(batch_size)
+        self.act = dnn_activation or "linear"
+        self.optimizer = optimizer
+        self.emb_opt = embedding_optimizer or ("adam_lazy" if optimizer == "adam" else "sgd")
+        self.lr, self.l2_embd, self.l2_dnn = float(lr), float(l2_embd), float(l2_dnn)
+        self.beta1, self.beta2, self.eps = 0.9, 0.999, 1e-7  # Keras Adam defaults
+        self.gemm_mode = gemm_mode
+        self.step_count = 0
+
+        # ---- lookup plan: ids columns are packed in field order, outputs follow the dense block ----
+        plan_fields, col = [], 0
+        for f, (ti, L, pool) in enumerate(fields):
+            plan_fields.append((ti, L, pool if (L > 1 or pool not in (None, "none")) else "none", col, self.nd_pad + f * self.D))
+            col += L
+        self.ids_cols = col
+        self.adam_m = self.adam_v = None
+        if self.emb_opt == "adam_lazy":
+            self.adam_m = [torch.zeros_like(t) for t in self.tables]
+            self.adam_v = [torch.zeros_like(t) for t in self.tables]
+        self.plan = K.LookupPlan(self.tables, plan_fields, self.adam_m, self.adam_v)
+
+        # ---- dense parameters: one flat buffer ----
+        self.K0 = self.n_dense + self.F * self.D           # logical DNN input width
+        self.K0p = self.nd_pad + self.F * self.D           # padded row width of X0
+        units = [self.K0] + [int(u) for u in dnn_hidden_units]  # core.py:57 prepends Dense(in)
+        self.units = units
+        self.layer_Kl = [self.K0] + units[:-1]                      # logical input widths
+        self.layer_ld = [_r4(u) if u > 1 else 1 for u in units]  # the 1-unit logit layer stays contiguous
+        self.layer_K = [self.K0p] + self.layer_ld[:-1]
+        offs, off, self._segments = [], 0, []
+        for Kp, ld in zip(self.layer_K, self.layer_ld):
+            wo = off
+            off = _r4(off + Kp * ld)
+            bo = off
+            off = _r4(off + ld)
+            offs.append((wo, bo))
+            self._segments.append((wo, bo - wo, True))   # kernel: l2_dnn applies (core.py:63)
+            self._segments.append((bo, off - bo, False))  # bias: no regulariser
+        self.fm_off = off
+        off += _r4(self.D + 1)
+        self._segments.append((self.fm_off, off - self.fm_off, False))
+        self.n_params = off
+        self.params = torch.zeros(off, device=self.dev, dtype=torch.float32)
+        self.grads = torch.zeros(off, device=self.dev, dtype=torch.float32)
+        self.opt_m = torch.zeros(off, device=self.dev, dtype=torch.float32) if optimizer == "adam" else None
+        self.opt_v = torch.zeros(off, device=self.dev, dtype=torch.float32) if optimizer == "adam" else None
+        self.W, self.b, self.dW, self.db = [], [], [], []
+        for (wo, bo), Kp, ld in zip(offs, self.layer_K, self.layer_ld):
+            self.W.append(self.params[wo : wo + Kp * ld].view(Kp, ld))
+            self.b.append(self.params[bo : bo + ld])
+            self.dW.append(self.grads[wo : wo + Kp * ld].view(Kp, ld))
+            self.db.append(self.grads[bo : bo + ld])
+        self.fm_w = self.params[self.fm_off : self.fm_off + self.D]
+        self.fm_w0 = self.params[self.fm_off + self.D : self.fm_off + self.D + 1]
+        self.d_fm = self.grads[self.fm_off : self.fm_off + self.D + 1]
+        self._init_dense(seed)
+
+        # ---- batch buffers ----
+        B = self.B
+        f32 = dict(device=self.dev, dtype=torch.float32)
+        self.X0 = torch.zeros(B, self.K0p, **f32)
+        self.A = [torch.zeros(B, ld, **f32) for ld in self.layer_ld]
+        self.dZ = [torch.zeros(B, ld, **f32) for ld in self.layer_ld]
+        self.dX0 = torch.zeros(B, self.K0p, **f32)
+        self.fm_out = torch.empty(B, **f32)
+        self.fm_sum = torch.empty(B, self.D, **f32)
+        self.prob = torch.empty(B, **f32)
+        self.loss_sum = torch.zeros(1, **f32)
+        self.ids_dev = torch.zeros(B, self.ids_cols, device=self.dev, dtype=torch.int32)
+        self.dense_dev = torch.zeros(B, max(self.n_dense, 1), **f32)
+        self.label_dev = torch.zeros(B, **f32)
+        self.loss_host = torch.zeros(1, dtype=torch.float32).pin_memory()
+        self._ws_emb = torch.empty(self.plan.workspace_bytes(B), device=self.dev, dtype=torch.uint8)
+
+    # ------------------------------------------------------------------------------------------
+    _marks = None  # when a list: (phase name, cuda event) recorded after every phase of a step
+
+    def _mark(self, name: str) -> None:
+        if self._marks is not None:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            self._marks.append((name, e))
+
+    def profile_step(self, ids, dense, label) -> "OrderedDict[str, float]":
+        """Run one train step with a CUDA event after every phase; returns ms per phase (launching stream)."""
+        from collections import OrderedDict
+
+        self._marks = []
+        self._mark("start")
+        self.train_step_on_device(ids, dense, label)
+        torch.cuda.current_stream().synchronize()
+        marks, self._marks = self._marks, None
+        out = OrderedDict()
+        for (n0, e0), (n1, e1) in zip(marks[:-1], marks[1:]):
+            out[n1] = out.get(n1, 0.0) + e0.elapsed_time(e1)
+        return out
+
+    def _init_dense(self, seed: int) -> None:
+        """Keras Dense defaults: glorot-uniform kernels, zero biases; FM Dense(1) glorot, w0 zeros."""
+        g = torch.Generator().manual_seed(seed)
+        for i, (Kl, u) in enumerate(zip(self.layer_Kl, self.units)):
+            lim = math.sqrt(6.0 / (Kl + u))
+            w = (torch.rand(Kl, u, generator=g) * 2 - 1) * lim
+            self.set_dense_weights(i, w, torch.zeros(u))
+        lim = math.sqrt(6.0 / (self.D + 1))
+        self.fm_w.copy_(((torch.rand(self.D, generator=g) * 2 - 1) * lim).to(self.dev))
+        self.fm_w0.zero_()
+
+    def set_dense_weights(self, i: int, w: torch.Tensor, b: torch.Tensor) -> None:
+        """w in the reference layout (K_logical, units): rows of layer 0 are [dense | embeddings]."""
+        Kl, u = self.layer_Kl[i], self.units[i]
+        assert tuple(w.shape) == (Kl, u) and tuple(b.shape) == (u,)
+        W = torch.zeros(self.layer_K[i], self.layer_ld[i])
+        if i == 0:
+            W[: self.n_dense, :u] = w[: self.n_dense]
+            W[self.nd_pad :, :u] = w[self.n_dense :]
+        else:
+            W[:Kl, :u] = w
+        self.W[i].copy_(W.to(self.dev))
+        bb = torch.zeros(self.layer_ld[i])
+        bb[:u] = b
+        self.b[i].copy_(bb.to(self.dev))
+
+    def get_dense_weights(self, i: int) -> Tuple[torch.Tensor, torch.Tensor]:
+        Kl, u = self.layer_Kl[i], self.units[i]
+        W = self.W[i].cpu()
+        if i == 0:
+            w = torch.cat([W[: self.n_dense, :u], W[self.nd_pad :, :u]], 0)
+        else:
+            w = W[:Kl, :u]
+        return w.clone(), self.b[i][:u].cpu().clone()
+
+    def get_dense_grads(self, i: int) -> Tuple[torch.Tensor, torch.Tensor]:
+        Kl, u = self.layer_Kl[i], self.units[i]
+        W = self.dW[i].cpu()
+        w = torch.cat([W[: self.n_dense, :u], W[self.nd_pad :, :u]], 0) if i == 0 else W[:Kl, :u]
+        return w.clone(), self.db[i][:u].cpu().clone()
+
+    # ------------------------------------------------------------------------------------------
+    def forward(self, ids: torch.Tensor, dense: Optional[torch.Tensor]) -> torch.Tensor:
+        """ids (B, ids_cols) int32, dense (B, n_dense) fp32|int32 on device -> logits in self.A[-1], probabilities."""
+        B = ids.shape[0]
+        assert B <= self.B
+        st = K._stream()
+        if self.n_dense:
+            call("hrb_pack_dense", K._p(dense), int(dense.dtype == torch.int32), dense.stride(0), B, self.n_dense, self.nd_pad,
+                 K._p(self.X0), self.K0p, st)
+            self._mark("pack_dense")
+        call("hrb_lookup_fm_fwd", self.plan._h, K._p(ids), ids.stride(0), B, K._p(self.X0), self.K0p, None, K._p(self.fm_w),
+             K._p(self.fm_w0), K._p(self.fm_out), K._p(self.fm_sum), None, st)
+        self._mark("lookup_fm_fwd")
+        x, ldx = self.X0, self.K0p
+        n = len(self.units)
+        for i in range(n):
+            act = self.act if i + 1 != n else "linear"  # core.py:66-69 with output_activation="linear"
+            call("hrb_dense_fwd", K._p(x), ldx, K._p(self.W[i]), self.layer_ld[i], K._p(self.b[i]), B, self.layer_K[i], self.units[i],
+                 _lib.ACT[act], K._p(self.A[i]), self.layer_ld[i], self.gemm_mode, st)
+            self._mark(f"dense_fwd_{i}")
+            x, ldx = self.A[i], self.layer_ld[i]
+        return self.A[-1]
+
+    def predict_on_device(self, ids: torch.Tensor, dense: Optional[torch.Tensor]) -> torch.Tensor:
+        B = ids.shape[0]
+        self.forward(ids, dense)
+        call("hrb_sigmoid_bce", K._p(self.A[-1]), K._p(self.fm_out), K._p(self.label_dev), B, 0.0, K._p(self.prob), None, None, K._stream())
+        return self.prob[:B]
+
+    def train_step_on_device(self, ids: torch.Tensor, dense: Optional[torch.Tensor], label: torch.Tensor) -> None:
+        """One full step: forward, BCE, backward, embedding row updates, dense optimiser.  Loss sum -> self.loss_sum."""
+        B = ids.shape[0]
+        st = K._stream()
+        self.step_count += 1
+        self.forward(ids, dense)
+        self.loss_sum.zero_()
+        dlogit = self.dZ[-1]  # (B, 1): the logit layer has one unit (DeepFM.py:59-60)
+        call("hrb_sigmoid_bce", K._p(self.A[-1]), K._p(self.fm_out), K._p(label), B, 1.0 / B, K._p(self.prob), K._p(dlogit), K._p(self.loss_sum), st)
+        self._mark("sigmoid_bce")
+        self._backward(ids, B, st)
+
+    def _backward(self, ids: torch.Tensor, B: int, st) -> None:
+        n = len(self.units)
+        need = ctypes.c_size_t(0)
+        dz, lddz = self.dZ[-1], self.layer_ld[-1]
+        for i in range(n - 1, -1, -1):
+            x, ldx = (self.A[i - 1], self.layer_ld[i - 1]) if i > 0 else (self.X0, self.K0p)
+            Kp, N = self.layer_K[i], self.units[i]
+            call("hrb_dense_bwd_w_workspace", B, Kp, N, ctypes.byref(need))
+            ws = self._dense_ws(need.value)
+            call("hrb_dense_bwd_w", K._p(x), ldx, K._p(dz), lddz, B, Kp, N, K._p(self.dW[i]), self.layer_ld[i], K._p(self.db[i]),
+                 K._p(ws), ws.numel(), self.gemm_mode, st)
+            self._mark(f"dense_bwd_w_{i}")
+            if i > 0:
+                call("hrb_dense_bwd_x", K._p(dz), lddz, K._p(self.W[i]), self.layer_ld[i], B, Kp, N, K._p(self.A[i - 1]), self.layer_ld[i - 1],
+                     _lib.ACT[self.act], K._p(self.dZ[i - 1]), self.layer_ld[i - 1], self.gemm_mode, st)
+                dz, lddz = self.dZ[i - 1], self.layer_ld[i - 1]
+            else:
+                call("hrb_dense_bwd_x", K._p(dz), lddz, K._p(self.W[0]), self.layer_ld[0], B, Kp, N, None, 0, 0, K._p(self.dX0), self.K0p,
+                     self.gemm_mode, st)
+            self._mark(f"dense_bwd_x_{i}")
+        # FM path adds dlogit * (w + S - x) into the embedding columns of dX0 (interaction.py:26-39)
+        emb_x = self.X0[:, self.nd_pad :]
+        emb_dx = self.dX0[:, self.nd_pad :]
+        call("hrb_fm_bwd", K._p(emb_x), self.K0p, B, self.F, self.D, K._p(self.fm_w), K._p(self.dZ[-1]), K._p(emb_dx), self.K0p, 1,
+             K._p(self.d_fm), st)
+        self._mark("fm_bwd")
+        # embedding rows: sort -> segment-reduce -> update (a13)
+        op = _lib.OptParams()
+        op.opt = _lib.OPT_SGD if self.emb_opt == "sgd" else _lib.OPT_ADAM_LAZY
+        op.lr, op.beta1, op.beta2, op.eps, op.l2_scale = self.lr, self.beta1, self.beta2, self.eps, 2.0 * self.l2_embd
+        op.bias_corr1, op.bias_corr2 = 1.0 - self.beta1 ** self.step_count, 1.0 - self.beta2 ** self.step_count
+        call("hrb_lookup_bwd_update", self.plan._h, K._p(ids), ids.stride(0), B, K._p(self.dX0), self.K0p, None, ctypes.byref(op),
+             K._p(self._ws_emb), self._ws_emb.numel(), st)
+        self._mark("embedding_bwd_update")
+        # dense parameters
+        segs = [(0, self.n_params, False)] if self.l2_dnn == 0.0 else self._segments
+        for off, length, reg in segs:
+            l2s = 2.0 * self.l2_dnn if reg else 0.0
+            o = off * 4
+            pp = lambda t: ctypes.c_void_p(t.data_ptr() + o)
+            if self.optimizer == "adam":
+                call("hrb_adam_step", pp(self.params), pp(self.grads), pp(self.opt_m), pp(self.opt_v), length, self.lr, self.beta1,
+                     self.beta2, self.eps, op.bias_corr1, op.bias_corr2, l2s, st)
+            else:
+                call("hrb_sgd_step", pp(self.params), pp(self.grads), length, self.lr, l2s, st)
+        self._mark("dense_optimizer")
+
+    _dws: Optional[torch.Tensor] = None
+
+    def _dense_ws(self, nbytes: int) -> torch.Tensor:
+        if self._dws is None or self._dws.numel() < nbytes:
+            self._dws = torch.empty(max(nbytes, 1 << 20), device=self.dev, dtype=torch.uint8)
+        return self._dws
+
+    # ------------------------------------------------------------------------------------------
+    # public, host-facing API (what Model.train_on_batch / predict call)
+    # ------------------------------------------------------------------------------------------
+    def train_on_batch(self, ids_host: torch.Tensor, dense_host: Optional[torch.Tensor], label_host: torch.Tensor) -> float:
+        """Host (pinned) tensors in, mean BCE loss out.  Includes the H2D copies and a D2H read of the loss."""
+        B = ids_host.shape[0]
+        self.ids_dev[:B].copy_(ids_host, non_blocking=True)
+        if self.n_dense:
+            self.dense_dev[:B].copy_(dense_host, non_blocking=True)
+        self.label_dev[:B].copy_(label_host, non_blocking=True)
+        self.train_step_on_device(self.ids_dev[:B], self.dense_dev[:B] if self.n_dense else None, self.label_dev[:B])
+        self.loss_host.copy_(self.loss_sum, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return float(self.loss_host[0]) / B
+
+    def predict(self, ids_host: torch.Tensor, dense_host: Optional[torch.Tensor]) -> torch.Tensor:
+        B = ids_host.shape[0]
+        self.ids_dev[:B].copy_(ids_host, non_blocking=True)
+        if self.n_dense:
+            self.dense_dev[:B].copy_(dense_host, non_blocking=True)
+        return self.predict_on_device(self.ids_dev[:B], self.dense_dev[:B] if self.n_dense else None).cpu().reshape(B, 1)
+
+    def h2d_bytes_per_step(self, B: int) -> int:
+        return B * (self.ids_cols * 4 + self.n_dense * 4 + 4)

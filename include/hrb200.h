@@ -53,6 +53,8 @@ typedef enum hrb_act {
 int hrb_abi_version(void);
 const char* hrb_status_str(int status);
 const char* hrb_last_error(void);
+/* number of CUDA kernels this library has launched in this process (every <<<>>> is counted) */
+int hrb_launch_count(int64_t* count);
 
 /* ------------------------------------------------------------------------------------------
  * Synthetic tables.  table[r,c] = lo + u*(hi-lo), u = (hash(seed, (row_start+r*row_step)*dim+c)>>8)*2^-24.
@@ -218,6 +220,11 @@ int hrb_lau_fwd(const float* table, int64_t vocab, int32_t dim, const int32_t* q
  * ------------------------------------------------------------------------------------------ */
 int hrb_sigmoid_bce(const float* dnn_logit, const float* fm_logit, const float* label, int64_t batch,
                     float grad_scale, float* prob, float* dlogit, float* loss_sum, void* stream);
+
+/* a8 concat glue (layers/utils.py:28-36,70-84): dense features (fp32, or int32 cast to fp32) go to the
+ * head columns of the DNN input row; columns [n, n_pad) are zero-filled (alignment padding). */
+int hrb_pack_dense(const void* src, int32_t src_is_int32, int64_t src_ld, int64_t batch, int32_t n, int32_t n_pad,
+                   float* dst, int64_t dst_ld, void* stream);
 
 /* Dense-parameter optimisers on a flat fp32 buffer (Keras Adam / SGD formulas). */
 int hrb_adam_step(float* param, const float* grad, float* m, float* v, int64_t n, float lr, float beta1,

@@ -241,7 +241,34 @@ static int launch_sgemm(const GemmArgs& g, int splits, cudaStream_t st) {
   return HRB_OK;
 }
 
+// 32x32 tiled transpose through shared memory: dst[c][r] = src[r][c]
+__global__ void __launch_bounds__(256) hrb_transpose_kernel(const float* __restrict__ src, int64_t rows, int32_t cols, int64_t lds,
+                                                        float* __restrict__ dst, int64_t ldd) {
+  __shared__ float tile[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  const int64_t r0 = (int64_t)blockIdx.y * 32;
+  const int c0 = blockIdx.x * 32;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int64_t r = r0 + ty + 8 * i;
+    tile[ty + 8 * i][tx] = (r < rows && c0 + tx < cols) ? src[r * lds + c0 + tx] : 0.f;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int c = c0 + ty + 8 * i;
+    if (c < cols && r0 + tx < rows) dst[(int64_t)c * ldd + r0 + tx] = tile[tx][ty + 8 * i];
+  }
+}
+
 // implemented in gemm_tc.cu (tcgen05 3xTF32); return HRB_UNSUPPORTED when the shape is not covered
+int hrb_tc_gemm_bias_act(const float* a, int64_t lda, const float* bt, int64_t ldb, const float* bias, int64_t M, int32_t N, int32_t K,
+                         int32_t act, float* c, int64_t ldc, float* ct, int64_t ldct, cudaStream_t st);
+int hrb_tc_gemm_act_grad(const float* a, int64_t lda, const float* bt, int64_t ldb, int64_t M, int32_t N, int32_t K, const float* aprev,
+                         int64_t ldap, int32_t act, float* c, int64_t ldc, float* ct, int64_t ldct, cudaStream_t st);
+int hrb_tc_splits(int64_t M, int32_t N, int32_t K);
+int hrb_tc_gemm_splitk(const float* a, int64_t lda, const float* bt, int64_t ldb, int64_t M, int32_t N, int32_t K, int32_t splits,
+                       float* part, int64_t ldp, cudaStream_t st);
 int hrb_tc_dense_fwd(const float* x, int64_t ldx, const float* w, int64_t ldw, const float* bias, int64_t M, int32_t K,
                      int32_t N, int32_t act, float* y, int64_t ldy, cudaStream_t st);
 int hrb_tc_dense_bwd_x(const float* dz, int64_t lddz, const float* w, int64_t ldw, int64_t M, int32_t K, int32_t N,
@@ -343,5 +370,77 @@ HRB_API int hrb_act_bwd(const float* y, const float* dy, int64_t n, int32_t act,
   const int64_t blocks = min((int64_t)sm_count() * 8, (n + 255) / 256);
   act_bwd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(y, dy, n, act, dz);
   HRB_LAUNCH_CHECK();
+  return HRB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// "TN" Dense entry points for the tcgen05 path: every operand has its reduction dim contiguous, so the
+// caller keeps transposed copies (W^T for the forward, x^T and dz^T for the weight gradient).
+// ---------------------------------------------------------------------------------------------
+HRB_API int hrb_transpose(const float* src, int64_t rows, int32_t cols, int64_t lds, float* dst, int64_t ldd, void* stream) {
+  HRB_REQUIRE(rows >= 0 && cols >= 0 && lds >= cols && ldd >= rows, "hrb_transpose: bad sizes");
+  if (rows == 0 || cols == 0) return HRB_OK;
+  HRB_REQUIRE(src && dst, "hrb_transpose: null pointer");
+  dim3 grid((cols + 31) / 32, (unsigned)((rows + 31) / 32));
+  HRB_REQUIRE(grid.y <= 65535u * 32u, "hrb_transpose: too many rows");
+  if (grid.y > 65535) return fail(HRB_UNSUPPORTED, "hrb_transpose: rows > 2M");
+  hrb_transpose_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, rows, cols, lds, dst, ldd);
+  HRB_LAUNCH_CHECK();
+  return HRB_OK;
+}
+
+HRB_API int hrb_dense_fwd_t(const float* x, int64_t ldx, const float* wt, int64_t ldwt, const float* bias, int64_t M, int32_t K,
+                            int32_t N, int32_t act, float* y, int64_t ldy, float* yt, int64_t ldyt, void* stream) {
+  HRB_REQUIRE(x && wt && y && M >= 0 && K > 0 && N > 0 && ldx >= K && ldwt >= K && ldy >= N, "hrb_dense_fwd_t: bad argument");
+  HRB_REQUIRE(yt == nullptr || ldyt >= M, "hrb_dense_fwd_t: ldyt < M");
+  HRB_REQUIRE(act >= HRB_ACT_LINEAR && act <= HRB_ACT_TANH, "hrb_dense_fwd_t: unknown activation %d", act);
+  if (M == 0) return HRB_OK;
+  return hrb_tc_gemm_bias_act(x, ldx, wt, ldwt, bias, M, N, K, act, y, ldy, yt, ldyt, (cudaStream_t)stream);
+}
+
+HRB_API int hrb_dense_bwd_x_t(const float* dz, int64_t lddz, const float* w, int64_t ldw, int64_t M, int32_t K, int32_t N,
+                              const float* a_prev, int64_t lda_prev, int32_t act_prev, float* dx, int64_t lddx, float* dxt,
+                              int64_t lddxt, void* stream) {
+  HRB_REQUIRE(dz && w && dx && M >= 0 && K > 0 && N > 0 && lddz >= N && ldw >= N && lddx >= K, "hrb_dense_bwd_x_t: bad argument");
+  HRB_REQUIRE(dxt == nullptr || lddxt >= M, "hrb_dense_bwd_x_t: lddxt < M");
+  if (M == 0) return HRB_OK;
+  return hrb_tc_gemm_act_grad(dz, lddz, w, ldw, M, K, N, a_prev, lda_prev, act_prev, dx, lddx, dxt, lddxt, (cudaStream_t)stream);
+}
+
+HRB_API int hrb_dense_bwd_w_t_workspace(int64_t M, int32_t K, int32_t N, size_t* bytes) {
+  HRB_REQUIRE(bytes && M >= 0 && K > 0 && N > 0, "hrb_dense_bwd_w_t_workspace: bad argument");
+  const int splits = hrb_tc_splits(K, N, (int32_t)(M > 0x7fffffff ? 0x7fffffff : M));
+  *bytes = (size_t)splits * K * (size_t)((N + 3) / 4 * 4) * sizeof(float) + (size_t)256 * N * sizeof(float) + 1024;
+  return HRB_OK;
+}
+
+// dw[K,N] = xt[K,M] * dzt[N,M]^T (split over M, fixed-order reduce); dbias[N] = column sums of dz[M,N]
+HRB_API int hrb_dense_bwd_w_t(const float* xt, int64_t ldxt, const float* dzt, int64_t lddzt, const float* dz, int64_t lddz, int64_t M,
+                              int32_t K, int32_t N, float* dw, int64_t lddw, float* dbias, void* workspace, size_t workspace_bytes,
+                              void* stream) {
+  HRB_REQUIRE(xt && dzt && dw && workspace && M > 0 && K > 0 && N > 0 && ldxt >= M && lddzt >= M && lddw >= N, "hrb_dense_bwd_w_t: bad argument");
+  HRB_REQUIRE(dbias == nullptr || (dz != nullptr && lddz >= N), "hrb_dense_bwd_w_t: dbias needs dz");
+  HRB_REQUIRE(M <= 0x7fffffff, "hrb_dense_bwd_w_t: M too large");
+  size_t need = 0;
+  hrb_dense_bwd_w_t_workspace(M, K, N, &need);
+  if (workspace_bytes < need) return fail(HRB_WORKSPACE, "hrb_dense_bwd_w_t: workspace %zu < required %zu bytes", workspace_bytes, need);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int splits = hrb_tc_splits(K, N, (int32_t)M);
+  const int64_t ldp = (N + 3) / 4 * 4;
+  float* part = (float*)workspace;
+  float* colpart = part + (size_t)splits * K * ldp;
+  int rc = hrb_tc_gemm_splitk(xt, ldxt, dzt, lddzt, K, N, (int32_t)M, splits, part, ldp, st);
+  if (rc != HRB_OK) return rc;
+  split_reduce_kernel<<<(unsigned)min((int64_t)sm_count() * 4, ((int64_t)K * N + 255) / 256), 256, 0, st>>>(part, K, N, ldp, splits, dw, lddw);
+  HRB_LAUNCH_CHECK();
+  if (dbias != nullptr) {
+    int yb = (int)min((int64_t)256, (M + 255) / 256);
+    const int64_t rpb = (M + yb - 1) / yb;
+    dim3 grid((N + 31) / 32, yb);
+    colsum_partial_kernel<<<grid, 256, 0, st>>>(dz, lddz, M, N, rpb, colpart);
+    HRB_LAUNCH_CHECK();
+    split_reduce_kernel<<<(N + 255) / 256, 256, 0, st>>>(colpart, 1, N, N, yb, dbias, N);
+    HRB_LAUNCH_CHECK();
+  }
   return HRB_OK;
 }

@@ -1,17 +1,442 @@
-// gemm_tc.cu -- tcgen05 (5th-gen tensor core) 3xTF32 error-compensated GEMM for the dense towers.
-// Placeholder entry points: until the tcgen05 path lands they report HRB_UNSUPPORTED and
-// hrb_dense_* (dense.cu) runs the fp32 FFMA kernel instead.
+// gemm_tc.cu -- tcgen05 (5th-gen tensor core) GEMM with 3xTF32 error compensation, used by the
+// Dense layers of the DNN towers (layers/core.py:53-78) when the problem is a real GEMM (M >= 1024).
+//
+//   C[M,N] = A[M,K] * Bt[N,K]^T      A, Bt row-major with the reduction dim contiguous ("K-major")
+//
+// fp32 parity (<= 1e-5 forward, <= 1e-4 gradients) rules out plain TF32 (10-bit mantissa).  Every fp32
+// operand tile is split in shared memory into hi = x & 0xFFFFE000 (exactly representable in TF32) and
+// lo = x - hi, and three MMAs accumulate hi*hi + lo*hi + hi*lo in TMEM (fp32): error ~2^-21, like FFMA.
+//
+// Persistent, warp-specialised (384 threads, 1 CTA/SM):
+//   warp 0      TMA producer   cp.async.bulk.tensor.2d (SWIZZLE_128B boxes of 32 fp32 = 128 B x rows)
+//   warp 1      MMA issuer     tcgen05.mma.cta_group::1.kind::tf32, 3 x (BK/8) instructions per k-block
+//   warp 2      TMEM allocator (2 accumulator stages x BN columns)
+//   warps 4-7   epilogue       tcgen05.ld 32x32b.x32 -> bias/activation/activation-gradient -> global
+//                              (row-major C and, optionally, the transposed copy Ct for the next bwd_w)
+//   warps 8-11  converters     hi/lo split of each landed stage, in place, fence.proxy.async
+// Pipelines: full (TMA->conv), conv (conv->MMA), empty (MMA->TMA, tcgen05.commit), tmem_full / tmem_empty.
+#include <cuda.h>
+
 #include "common.cuh"
 
-int hrb_tc_dense_fwd(const float*, int64_t, const float*, int64_t, const float*, int64_t, int32_t, int32_t, int32_t,
-                     float*, int64_t, cudaStream_t) {
-  return hrb::fail(HRB_UNSUPPORTED, "tcgen05 GEMM path not built for this shape");
+namespace hrb {
+namespace tc {
+
+constexpr int BM = 128;
+constexpr int BK = 32;  // 32 fp32 = 128 bytes = one SWIZZLE_128B span
+constexpr int STAGES = 3;
+constexpr int THREADS = 384;
+constexpr int EPI_WARP0 = 4, CONV_WARP0 = 8;
+
+enum { EPI_BIAS_ACT = 0, EPI_ACT_GRAD = 1, EPI_PLAIN = 2 };
+
+__device__ __forceinline__ uint32_t s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s32(bar)), "r"(count));
 }
-int hrb_tc_dense_bwd_x(const float*, int64_t, const float*, int64_t, int64_t, int32_t, int32_t, const float*, int64_t,
-                       int32_t, float*, int64_t, cudaStream_t) {
-  return hrb::fail(HRB_UNSUPPORTED, "tcgen05 GEMM path not built for this shape");
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s32(bar)) : "memory");
 }
-int hrb_tc_dense_bwd_w(const float*, int64_t, const float*, int64_t, int64_t, int32_t, int32_t, float*, int64_t, void*,
-                       size_t, cudaStream_t) {
-  return hrb::fail(HRB_UNSUPPORTED, "tcgen05 GEMM path not built for this shape");
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+      : "=r"(ok)
+      : "r"(s32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// bounded wait: a protocol bug becomes a trap (CUDA error) instead of a hung GPU
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try(bar, parity))
+    if (clock64() - t0 > 8000000000LL) __trap();
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(s32(dst)),
+      "l"(map), "r"(s32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
+//   [0,14) start>>4 | [16,30) LBO>>4 (unused for swizzled K-major) | [32,46) SBO>>4 = 1024 B between
+//   8-row groups | [46,48) version = 1 (sm100) | [61,64) layout = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_desc(const void* smem) {
+  uint64_t d = 0;
+  d |= (uint64_t)((s32(smem) >> 4) & 0x3FFF);
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+struct Args {
+  float* C;
+  float* Ct;           // optional transposed copy [N][ldct]
+  const float* bias;   // EPI_BIAS_ACT
+  const float* aprev;  // EPI_ACT_GRAD: previous layer's post-activation output [M][ldap]
+  int64_t ldc, ldct, ldap;
+  int64_t M;
+  int32_t N, K;
+  int32_t act;
+  int32_t splits;      // split over K (EPI_PLAIN): slice z writes C + z*M*ldc
+  int32_t kb_per_split;
+};
+
+template <int BN, int EPI>
+__global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a,
+                                                             const __grid_constant__ CUtensorMap map_b, Args g) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  constexpr uint32_t A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4;
+  constexpr uint32_t STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;  // A_hi | A_lo | B_hi | B_lo
+  // 1024-byte alignment of every tile (SWIZZLE_128B atoms are 8 rows x 128 B)
+  unsigned char* tiles = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ __align__(8) uint64_t full_bar[STAGES], conv_bar[STAGES], empty_bar[STAGES], tfull_bar[2], tempty_bar[2];
+  __shared__ uint32_t tmem_base_smem;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m_tiles = (int)((g.M + BM - 1) / BM), n_tiles = (g.N + BN - 1) / BN;
+  const int64_t n_work = (int64_t)m_tiles * n_tiles * g.splits;
+  const int kb_total = (g.K + BK - 1) / BK;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&conv_bar[s], 128);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull_bar[a], 1);
+      mbar_init(&tempty_bar[a], 128);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {  // one warp allocates 2 accumulator stages (power of two >= 32 columns)
+    constexpr uint32_t cols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(&tmem_base_smem)), "n"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  // work item -> (m tile, n tile, k split); n fastest so neighbouring CTAs share the A rows in L2
+  auto decode = [&](int64_t w, int& mt, int& nt, int& z) {
+    z = (int)(w / ((int64_t)m_tiles * n_tiles));
+    const int64_t r = w - (int64_t)z * m_tiles * n_tiles;
+    mt = (int)(r / n_tiles);
+    nt = (int)(r - (int64_t)mt * n_tiles);
+  };
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int64_t w = blockIdx.x; w < n_work; w += gridDim.x) {
+        int mt, nt, z;
+        decode(w, mt, nt, z);
+        const int kb0 = z * g.kb_per_split, kb1 = min(kb_total, kb0 + g.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
+          const int s = it % STAGES;
+          mbar_wait(&empty_bar[s], ((it / STAGES) & 1) ^ 1);
+          unsigned char* st = tiles + (size_t)s * STAGE_BYTES;
+          mbar_expect_tx(&full_bar[s], A_BYTES + B_BYTES);
+          tma_load_2d(st, &map_a, &full_bar[s], kb * BK, mt * BM);
+          tma_load_2d(st + 2 * A_BYTES, &map_b, &full_bar[s], kb * BK, nt * BN);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      // instruction descriptor (cute::UMMA::InstrDescriptor): c=F32 [4,6), a=b=TF32 [7,10)/[10,13),
+      // K-major A and B (bits 15,16 = 0), N>>3 at [17,23), M>>4 at [24,29)
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      uint32_t it = 0, tcount = 0;
+      for (int64_t w = blockIdx.x; w < n_work; w += gridDim.x, ++tcount) {
+        int mt, nt, z;
+        decode(w, mt, nt, z);
+        const int kb0 = z * g.kb_per_split, kb1 = min(kb_total, kb0 + g.kb_per_split);
+        const int a = tcount & 1;
+        mbar_wait(&tempty_bar[a], ((tcount >> 1) & 1) ^ 1);  // epilogue drained this accumulator
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(a * BN);
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
+          const int s = it % STAGES;
+          mbar_wait(&conv_bar[s], (it / STAGES) & 1);
+          tc_fence_after();
+          unsigned char* st = tiles + (size_t)s * STAGE_BYTES;
+          const uint64_t a_hi = make_desc(st), a_lo = make_desc(st + A_BYTES);
+          const uint64_t b_hi = make_desc(st + 2 * A_BYTES), b_lo = make_desc(st + 2 * A_BYTES + B_BYTES);
+#pragma unroll
+          for (int kk = 0; kk < BK / 8; ++kk) {  // UMMA_K = 8 tf32 = 32 bytes: +2 in the (>>4) start-address field
+            const uint64_t o = (uint64_t)(kk * 2);
+            umma_tf32(tmem_d, a_lo + o, b_hi + o, idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
+            umma_tf32(tmem_d, a_hi + o, b_lo + o, idesc, 1u);
+            umma_tf32(tmem_d, a_hi + o, b_hi + o, idesc, 1u);
+          }
+          umma_commit(&empty_bar[s]);  // frees the smem stage once these MMAs retire
+        }
+        umma_commit(&tfull_bar[a]);    // accumulator complete -> epilogue
+      }
+    }
+  } else if (warp >= CONV_WARP0) {
+    // ===================== converters: hi/lo split in place =====================
+    const int t = threadIdx.x - CONV_WARP0 * 32;  // 0..127
+    uint32_t it = 0;
+    for (int64_t w = blockIdx.x; w < n_work; w += gridDim.x) {
+      int mt, nt, z;
+      decode(w, mt, nt, z);
+      const int kb0 = z * g.kb_per_split, kb1 = min(kb_total, kb0 + g.kb_per_split);
+      for (int kb = kb0; kb < kb1; ++kb, ++it) {
+        const int s = it % STAGES;
+        mbar_wait(&full_bar[s], (it / STAGES) & 1);
+        unsigned char* st = tiles + (size_t)s * STAGE_BYTES;
+        // element-wise, so the swizzled placement is irrelevant: lo lands at the same offset as hi
+#pragma unroll 4
+        for (int i = t; i < (int)(A_BYTES / 16); i += 128) {
+          float4* p = reinterpret_cast<float4*>(st) + i;
+          float4 x = *p, h;
+          h.x = __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u);
+          h.y = __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u);
+          h.z = __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u);
+          h.w = __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u);
+          *p = h;
+          reinterpret_cast<float4*>(st + A_BYTES)[i] = make_float4(x.x - h.x, x.y - h.y, x.z - h.z, x.w - h.w);
+        }
+#pragma unroll 4
+        for (int i = t; i < (int)(B_BYTES / 16); i += 128) {
+          float4* p = reinterpret_cast<float4*>(st + 2 * A_BYTES) + i;
+          float4 x = *p, h;
+          h.x = __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u);
+          h.y = __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u);
+          h.z = __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u);
+          h.w = __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u);
+          *p = h;
+          reinterpret_cast<float4*>(st + 2 * A_BYTES + B_BYTES)[i] = make_float4(x.x - h.x, x.y - h.y, x.z - h.z, x.w - h.w);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to UMMA
+        mbar_arrive(&conv_bar[s]);
+      }
+    }
+  } else if (warp >= EPI_WARP0 && warp < EPI_WARP0 + 4) {
+    // ===================== epilogue =====================
+    const int q = warp - EPI_WARP0;  // == warp % 4: the TMEM lane quadrant this warp may read
+    uint32_t tcount = 0;
+    for (int64_t w = blockIdx.x; w < n_work; w += gridDim.x, ++tcount) {
+      int mt, nt, z;
+      decode(w, mt, nt, z);
+      const int a = tcount & 1;
+      mbar_wait(&tfull_bar[a], (tcount >> 1) & 1);
+      tc_fence_after();
+      const int64_t m = (int64_t)mt * BM + q * 32 + lane;
+      const bool row_ok = m < g.M;
+      float* crow = g.C + (int64_t)z * g.M * g.ldc + m * g.ldc;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t r[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * BN + c0);
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,"
+            "%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+              "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]),
+              "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]),
+              "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+            : "r"(taddr));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        const int n0 = nt * BN + c0;
+        if (n0 < g.N) {
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          if (row_ok) {
+            if (EPI == EPI_BIAS_ACT) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (n0 + j < g.N) v[j] = act_apply(g.act, v[j] + (g.bias != nullptr ? __ldg(g.bias + n0 + j) : 0.f));
+            } else if (EPI == EPI_ACT_GRAD) {
+              if (g.aprev != nullptr) {
+                const float* ap = g.aprev + m * g.ldap + n0;
+#pragma unroll
+                for (int j4 = 0; j4 < 32; j4 += 4) {
+                  if (n0 + j4 + 3 < g.N) {
+                    const float4 y = __ldg(reinterpret_cast<const float4*>(ap + j4));
+                    v[j4] *= act_grad_from_out(g.act, y.x); v[j4 + 1] *= act_grad_from_out(g.act, y.y);
+                    v[j4 + 2] *= act_grad_from_out(g.act, y.z); v[j4 + 3] *= act_grad_from_out(g.act, y.w);
+                  } else {
+                    for (int j = j4; j < j4 + 4; ++j)
+                      if (n0 + j < g.N) v[j] *= act_grad_from_out(g.act, __ldg(ap + j));
+                  }
+                }
+              }
+            }
+#pragma unroll
+            for (int j4 = 0; j4 < 32; j4 += 4) {
+              if (n0 + j4 + 3 < g.N) {
+                *reinterpret_cast<float4*>(crow + n0 + j4) = make_float4(v[j4], v[j4 + 1], v[j4 + 2], v[j4 + 3]);
+              } else {
+                for (int j = j4; j < j4 + 4; ++j)
+                  if (n0 + j < g.N) crow[n0 + j] = v[j];
+              }
+            }
+          }
+          if (g.Ct != nullptr) {  // transposed copy: for a fixed column the 32 lanes write 32 consecutive m
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (row_ok && n0 + j < g.N) g.Ct[(int64_t)(n0 + j) * g.ldct + m] = v[j];
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty_bar[a]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    constexpr uint32_t cols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(cols) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+// 2-D fp32 row-major [rows][cols] with leading dim ld; box = 32 columns (128 B) x box_rows, SWIZZLE_128B
+static int make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (fn == nullptr) return fail(HRB_CUDA_ERROR, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(HRB_CUDA_ERROR, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return HRB_OK;
+}
+
+template <int BN, int EPI>
+static int launch(const float* A, int64_t lda, const float* Bt, int64_t ldb, const Args& g, cudaStream_t st) {
+  CUtensorMap ma, mb;
+  int rc = make_map(&ma, A, g.M, g.K, lda, BM);
+  if (rc != HRB_OK) return rc;
+  rc = make_map(&mb, Bt, g.N, g.K, ldb, BN);
+  if (rc != HRB_OK) return rc;
+  constexpr size_t smem = (size_t)STAGES * (2 * BM * BK * 4 + 2 * BN * BK * 4) + 1024;
+  static bool attr_done = false;
+  if (!attr_done) {
+    HRB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_done = true;
+  }
+  const int64_t work = (int64_t)((g.M + BM - 1) / BM) * ((g.N + BN - 1) / BN) * g.splits;
+  int64_t grid = work < sm_count() ? work : sm_count();
+  gemm_tc_kernel<BN, EPI><<<(unsigned)grid, THREADS, smem, st>>>(ma, mb, g);
+  HRB_LAUNCH_CHECK();
+  return HRB_OK;
+}
+
+static bool tc_ok(const float* A, int64_t lda, const float* Bt, int64_t ldb, int64_t M, int32_t N, int32_t K) {
+  // TMA needs 16-byte aligned bases and row pitches; tiny problems stay on the FFMA kernel
+  return aligned16(A) && aligned16(Bt) && lda % 4 == 0 && ldb % 4 == 0 && M >= 512 && N >= 16 && K >= 16;
+}
+
+}  // namespace tc
+}  // namespace hrb
+
+using namespace hrb;
+
+// Internal entry points (exported through dense.cu): all operands "TN" = reduction dim contiguous.
+// C[M,N] = act(A[M,K] * Bt[N,K]^T + bias)  (+ transposed copy Ct[N,M])
+int hrb_tc_gemm_bias_act(const float* a, int64_t lda, const float* bt, int64_t ldb, const float* bias, int64_t M, int32_t N, int32_t K,
+                         int32_t act, float* c, int64_t ldc, float* ct, int64_t ldct, cudaStream_t st) {
+  if (!tc::tc_ok(a, lda, bt, ldb, M, N, K) || !aligned16(c) || ldc % 4 != 0)
+    return fail(HRB_UNSUPPORTED, "tcgen05 GEMM: shape/alignment not covered");
+  tc::Args g{c, ct, bias, nullptr, ldc, ldct, 0, M, N, K, act, 1, (K + tc::BK - 1) / tc::BK};
+  return tc::launch<128, tc::EPI_BIAS_ACT>(a, lda, bt, ldb, g, st);
+}
+// C[M,N] = (A[M,K] * Bt[N,K]^T) * act'(aprev[M,N])  (+ transposed copy)
+int hrb_tc_gemm_act_grad(const float* a, int64_t lda, const float* bt, int64_t ldb, int64_t M, int32_t N, int32_t K, const float* aprev,
+                         int64_t ldap, int32_t act, float* c, int64_t ldc, float* ct, int64_t ldct, cudaStream_t st) {
+  if (!tc::tc_ok(a, lda, bt, ldb, M, N, K) || !aligned16(c) || ldc % 4 != 0 || (aprev != nullptr && (!aligned16(aprev) || ldap % 4 != 0)))
+    return fail(HRB_UNSUPPORTED, "tcgen05 GEMM: shape/alignment not covered");
+  tc::Args g{c, ct, nullptr, aprev, ldc, ldct, ldap, M, N, K, act, 1, (K + tc::BK - 1) / tc::BK};
+  return tc::launch<128, tc::EPI_ACT_GRAD>(a, lda, bt, ldb, g, st);
+}
+// split-K partials: part[z][M][ldp] = A[M, Kz] * Bt[N, Kz]^T ; the caller reduces over z in fixed order
+int hrb_tc_splits(int64_t M, int32_t N, int32_t K) {
+  const int tiles = (int)((M + tc::BM - 1) / tc::BM) * ((N + 127) / 128);
+  const int kb_total = (K + tc::BK - 1) / tc::BK;
+  int splits = sm_count() / (tiles > 0 ? tiles : 1);
+  if (splits < 1) splits = 1;
+  if (splits > kb_total) splits = kb_total;
+  const int per = (kb_total + splits - 1) / splits;
+  return (kb_total + per - 1) / per;
+}
+int hrb_tc_gemm_splitk(const float* a, int64_t lda, const float* bt, int64_t ldb, int64_t M, int32_t N, int32_t K, int32_t splits,
+                       float* part, int64_t ldp, cudaStream_t st) {
+  if (!(aligned16(a) && aligned16(bt) && lda % 4 == 0 && ldb % 4 == 0 && aligned16(part) && ldp % 4 == 0 && K >= 64))
+    return fail(HRB_UNSUPPORTED, "tcgen05 split-K GEMM: shape/alignment not covered");
+  const int kb_total = (K + tc::BK - 1) / tc::BK;
+  const int per = (kb_total + splits - 1) / splits;
+  if ((kb_total + per - 1) / per != splits) return fail(HRB_BAD_ARG, "tcgen05 split-K GEMM: %d splits leave empty slices", splits);
+  tc::Args g{part, nullptr, nullptr, nullptr, ldp, 0, 0, M, N, K, 0, splits, per};
+  return tc::launch<128, tc::EPI_PLAIN>(a, lda, bt, ldb, g, st);
+}
+
+// ---- hooks used by dense.cu (row-major weight layouts of hrb_dense_*) ---------------------------------------
+// The Dense entry points take W[K,N] (N contiguous).  Only bwd_x has both operands K-major as stored; fwd needs
+// W^T and bwd_w needs x^T / dz^T, which the engine keeps as transposed copies and feeds to hrb_gemm_tn_* directly.
+int hrb_tc_dense_fwd(const float*, int64_t, const float*, int64_t, const float*, int64_t, int32_t, int32_t, int32_t, float*, int64_t,
+                     cudaStream_t) {
+  return hrb::fail(HRB_UNSUPPORTED, "tcgen05 forward needs the transposed weight: call hrb_gemm_tn_bias_act");
+}
+int hrb_tc_dense_bwd_x(const float* dz, int64_t lddz, const float* w, int64_t ldw, int64_t M, int32_t K, int32_t N, const float* a_prev,
+                       int64_t lda_prev, int32_t act_prev, float* dx, int64_t lddx, cudaStream_t st) {
+  // dx[M,K] = dz[M,N] * w[K,N]^T: A = dz (N contiguous), Bt = w (K rows, N contiguous) -> exactly the TN form
+  if (!tc::tc_ok(dz, lddz, w, ldw, M, K, N)) return hrb::fail(HRB_UNSUPPORTED, "tcgen05 bwd_x: shape/alignment not covered");
+  if (a_prev != nullptr && !(aligned16(a_prev) && lda_prev % 4 == 0)) return hrb::fail(HRB_UNSUPPORTED, "tcgen05 bwd_x: a_prev alignment");
+  if (!(aligned16(dx) && lddx % 4 == 0)) return hrb::fail(HRB_UNSUPPORTED, "tcgen05 bwd_x: dx alignment");
+  tc::Args g{dx, nullptr, nullptr, a_prev, lddx, 0, lda_prev, M, K, N, act_prev, 1, (N + tc::BK - 1) / tc::BK};
+  return tc::launch<128, tc::EPI_ACT_GRAD>(dz, lddz, w, ldw, g, st);
+}
+int hrb_tc_dense_bwd_w(const float*, int64_t, const float*, int64_t, int64_t, int32_t, int32_t, float*, int64_t, void*, size_t,
+                       cudaStream_t) {
+  return hrb::fail(HRB_UNSUPPORTED, "tcgen05 bwd_w needs transposed activations: call hrb_gemm_tn_splitk");
 }

@@ -383,3 +383,57 @@ def adam_step(param, grad, m, v, lr, beta1=0.9, beta2=0.999, eps=1e-7, step=1, l
 
 def sgd_step(param, grad, lr, l2_scale=0.0):
     call("hrb_sgd_step", _p(param), _p(grad), param.numel(), lr, l2_scale, _stream())
+
+
+# --------------------------------------------------------------------------------------------
+# tcgen05 "TN" Dense variants (3xTF32): every operand has its reduction dim contiguous
+# --------------------------------------------------------------------------------------------
+def transpose(src: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    rows, cols = src.shape
+    if out is None:
+        out = torch.empty(cols, rows, device=src.device, dtype=torch.float32)
+    call("hrb_transpose", _p(src), rows, cols, _row_major_2d(src, "src"), _p(out), _row_major_2d(out, "out"), _stream())
+    return out
+
+
+def dense_fwd_t(x, wt, bias, act=None, out=None, out_t=None):
+    """y = act(x @ wt.T + bias); wt is (N, K).  out_t (N, M) optionally receives y^T."""
+    M, Kd = x.shape
+    N = wt.shape[0]
+    if out is None:
+        out = torch.empty(M, N, device=x.device, dtype=torch.float32)
+    call("hrb_dense_fwd_t", _p(x), _row_major_2d(x, "x"), _p(wt), _row_major_2d(wt, "wt"), _p(bias), M, Kd, N, ACT[act], _p(out),
+         _row_major_2d(out, "out"), _p(out_t), _row_major_2d(out_t, "out_t") if out_t is not None else 0, _stream())
+    return out
+
+
+def dense_bwd_x_t(dz, w, a_prev=None, act_prev=None, out=None, out_t=None):
+    """dx = (dz @ w.T) * act'(a_prev); w is (K, N) row-major as in the forward."""
+    M, N = dz.shape
+    Kd = w.shape[0]
+    if out is None:
+        out = torch.empty(M, Kd, device=dz.device, dtype=torch.float32)
+    call("hrb_dense_bwd_x_t", _p(dz), _row_major_2d(dz, "dz"), _p(w), _row_major_2d(w, "w"), M, Kd, N, _p(a_prev),
+         _row_major_2d(a_prev, "a_prev") if a_prev is not None else 0, ACT[act_prev], _p(out), _row_major_2d(out, "out"), _p(out_t),
+         _row_major_2d(out_t, "out_t") if out_t is not None else 0, _stream())
+    return out
+
+
+def dense_bwd_w_t(xt, dzt, dz=None, dw=None, dbias=None):
+    """dw (K, N) = xt (K, M) @ dzt (N, M).T ; dbias = column sums of dz (M, N)."""
+    Kd, M = xt.shape
+    N = dzt.shape[0]
+    need = ctypes.c_size_t(0)
+    call("hrb_dense_bwd_w_t_workspace", M, Kd, N, ctypes.byref(need))
+    key = ("t", xt.device.index, torch.cuda.current_stream().cuda_stream)
+    ws = _dense_ws.get(key)
+    if ws is None or ws.numel() < need.value:
+        ws = torch.empty(need.value, device=xt.device, dtype=torch.uint8)
+        _dense_ws[key] = ws
+    if dw is None:
+        dw = torch.empty(Kd, N, device=xt.device, dtype=torch.float32)
+    if dbias is None and dz is not None:
+        dbias = torch.empty(N, device=xt.device, dtype=torch.float32)
+    call("hrb_dense_bwd_w_t", _p(xt), _row_major_2d(xt, "xt"), _p(dzt), _row_major_2d(dzt, "dzt"), _p(dz),
+         _row_major_2d(dz, "dz") if dz is not None else 0, M, Kd, N, _p(dw), _row_major_2d(dw, "dw"), _p(dbias), _p(ws), ws.numel(), _stream())
+    return dw, dbias

@@ -146,6 +146,15 @@ class DeepFMEngine:
         self.fm_sum = torch.empty(B, self.D, **f32)
         self.prob = torch.empty(B, **f32)
         self.loss_sum = torch.zeros(1, **f32)
+        # tcgen05 path: transposed copies so that every GEMM operand has its reduction dim contiguous
+        self.use_tc = gemm_mode != _lib.GEMM_FP32 and B >= 512 and B % 4 == 0
+        self.tc_layer = [self.use_tc and u >= 16 for u in self.units]
+        if self.use_tc:
+            self.Wt = [torch.zeros(ld, Kp, **f32) if tc else None for ld, Kp, tc in zip(self.layer_ld, self.layer_K, self.tc_layer)]
+            self.X0t = torch.zeros(self.K0p, B, **f32)
+            self.At = [torch.zeros(ld, B, **f32) for ld in self.layer_ld]
+            self.dZt = [torch.zeros(ld, B, **f32) for ld in self.layer_ld]
+            self._refresh_wt()
         self.ids_dev = torch.zeros(B, self.ids_cols, device=self.dev, dtype=torch.int32)
         self.dense_dev = torch.zeros(B, max(self.n_dense, 1), **f32)
         self.label_dev = torch.zeros(B, **f32)
@@ -175,6 +184,15 @@ class DeepFMEngine:
             out[n1] = out.get(n1, 0.0) + e0.elapsed_time(e1)
         return out
 
+    def _refresh_wt(self) -> None:
+        """W_i^T for the tensor-core forward (the optimiser updates W_i; 1.3 MB of transposes per step)."""
+        if not getattr(self, "use_tc", False):
+            return
+        st = K._stream()
+        for i, tc in enumerate(self.tc_layer):
+            if tc:
+                call("hrb_transpose", K._p(self.W[i]), self.layer_K[i], self.layer_ld[i], self.layer_ld[i], K._p(self.Wt[i]), self.layer_K[i], st)
+
     def _init_dense(self, seed: int) -> None:
         """Keras Dense defaults: glorot-uniform kernels, zero biases; FM Dense(1) glorot, w0 zeros."""
         g = torch.Generator().manual_seed(seed)
@@ -200,6 +218,7 @@ class DeepFMEngine:
         bb = torch.zeros(self.layer_ld[i])
         bb[:u] = b
         self.b[i].copy_(bb.to(self.dev))
+        self._refresh_wt()
 
     def get_dense_weights(self, i: int) -> Tuple[torch.Tensor, torch.Tensor]:
         Kl, u = self.layer_Kl[i], self.units[i]
@@ -217,7 +236,7 @@ class DeepFMEngine:
         return w.clone(), self.db[i][:u].cpu().clone()
 
     # ------------------------------------------------------------------------------------------
-    def forward(self, ids: torch.Tensor, dense: Optional[torch.Tensor]) -> torch.Tensor:
+    def forward(self, ids: torch.Tensor, dense: Optional[torch.Tensor], training: bool = False) -> torch.Tensor:
         """ids (B, ids_cols) int32, dense (B, n_dense) fp32|int32 on device -> logits in self.A[-1], probabilities."""
         B = ids.shape[0]
         assert B <= self.B
@@ -233,8 +252,14 @@ class DeepFMEngine:
         n = len(self.units)
         for i in range(n):
             act = self.act if i + 1 != n else "linear"  # core.py:66-69 with output_activation="linear"
-            call("hrb_dense_fwd", K._p(x), ldx, K._p(self.W[i]), self.layer_ld[i], K._p(self.b[i]), B, self.layer_K[i], self.units[i],
-                 _lib.ACT[act], K._p(self.A[i]), self.layer_ld[i], self.gemm_mode, st)
+            if self.use_tc and self.tc_layer[i] and B == self.B:
+                call("hrb_dense_fwd_t", K._p(x), ldx, K._p(self.Wt[i]), self.layer_K[i], K._p(self.b[i]), B, self.layer_K[i], self.units[i],
+                     _lib.ACT[act], K._p(self.A[i]), self.layer_ld[i], K._p(self.At[i]) if training else None, B, st)
+            else:
+                call("hrb_dense_fwd", K._p(x), ldx, K._p(self.W[i]), self.layer_ld[i], K._p(self.b[i]), B, self.layer_K[i], self.units[i],
+                     _lib.ACT[act], K._p(self.A[i]), self.layer_ld[i], _lib.GEMM_FP32, st)
+                if training and self.use_tc and B == self.B and i + 1 != n:  # a later tensor-core bwd_w reads A_i^T
+                    call("hrb_transpose", K._p(self.A[i]), B, self.units[i], self.layer_ld[i], K._p(self.At[i]), B, st)
             self._mark(f"dense_fwd_{i}")
             x, ldx = self.A[i], self.layer_ld[i]
         return self.A[-1]
@@ -250,7 +275,7 @@ class DeepFMEngine:
         B = ids.shape[0]
         st = K._stream()
         self.step_count += 1
-        self.forward(ids, dense)
+        self.forward(ids, dense, training=True)
         self.loss_sum.zero_()
         dlogit = self.dZ[-1]  # (B, 1): the logit layer has one unit (DeepFM.py:59-60)
         call("hrb_sigmoid_bce", K._p(self.A[-1]), K._p(self.fm_out), K._p(label), B, 1.0 / B, K._p(self.prob), K._p(dlogit), K._p(self.loss_sum), st)
@@ -261,21 +286,43 @@ class DeepFMEngine:
         n = len(self.units)
         need = ctypes.c_size_t(0)
         dz, lddz = self.dZ[-1], self.layer_ld[-1]
+        tc_step = self.use_tc and B == self.B
+        if tc_step:
+            call("hrb_transpose", K._p(self.X0), B, self.K0p, self.K0p, K._p(self.X0t), B, st)
+            self._mark("transpose_x0")
         for i in range(n - 1, -1, -1):
             x, ldx = (self.A[i - 1], self.layer_ld[i - 1]) if i > 0 else (self.X0, self.K0p)
             Kp, N = self.layer_K[i], self.units[i]
+            if tc_step and self.tc_layer[i]:
+                xt = self.At[i - 1] if i > 0 else self.X0t
+                call("hrb_dense_bwd_w_t_workspace", B, Kp, N, ctypes.byref(need))
+                ws = self._dense_ws(need.value)
+                call("hrb_dense_bwd_w_t", K._p(xt), B, K._p(self.dZt[i]), B, K._p(dz), lddz, B, Kp, N, K._p(self.dW[i]), self.layer_ld[i],
+                     K._p(self.db[i]), K._p(ws), ws.numel(), st)
+                self._mark(f"dense_bwd_w_{i}")
+                if i > 0:
+                    call("hrb_dense_bwd_x_t", K._p(dz), lddz, K._p(self.W[i]), self.layer_ld[i], B, Kp, N, K._p(self.A[i - 1]), self.layer_ld[i - 1],
+                         _lib.ACT[self.act], K._p(self.dZ[i - 1]), self.layer_ld[i - 1], K._p(self.dZt[i - 1]), B, st)
+                    dz, lddz = self.dZ[i - 1], self.layer_ld[i - 1]
+                else:
+                    call("hrb_dense_bwd_x_t", K._p(dz), lddz, K._p(self.W[0]), self.layer_ld[0], B, Kp, N, None, 0, 0, K._p(self.dX0), self.K0p,
+                         None, 0, st)
+                self._mark(f"dense_bwd_x_{i}")
+                continue
             call("hrb_dense_bwd_w_workspace", B, Kp, N, ctypes.byref(need))
             ws = self._dense_ws(need.value)
             call("hrb_dense_bwd_w", K._p(x), ldx, K._p(dz), lddz, B, Kp, N, K._p(self.dW[i]), self.layer_ld[i], K._p(self.db[i]),
-                 K._p(ws), ws.numel(), self.gemm_mode, st)
+                 K._p(ws), ws.numel(), _lib.GEMM_FP32, st)
             self._mark(f"dense_bwd_w_{i}")
             if i > 0:
                 call("hrb_dense_bwd_x", K._p(dz), lddz, K._p(self.W[i]), self.layer_ld[i], B, Kp, N, K._p(self.A[i - 1]), self.layer_ld[i - 1],
-                     _lib.ACT[self.act], K._p(self.dZ[i - 1]), self.layer_ld[i - 1], self.gemm_mode, st)
+                     _lib.ACT[self.act], K._p(self.dZ[i - 1]), self.layer_ld[i - 1], _lib.GEMM_FP32, st)
                 dz, lddz = self.dZ[i - 1], self.layer_ld[i - 1]
+                if tc_step:  # the next (tensor-core) weight gradient wants dz^T
+                    call("hrb_transpose", K._p(dz), B, self.units[i - 1], lddz, K._p(self.dZt[i - 1]), B, st)
             else:
                 call("hrb_dense_bwd_x", K._p(dz), lddz, K._p(self.W[0]), self.layer_ld[0], B, Kp, N, None, 0, 0, K._p(self.dX0), self.K0p,
-                     self.gemm_mode, st)
+                     _lib.GEMM_FP32, st)
             self._mark(f"dense_bwd_x_{i}")
         # FM path adds dlogit * (w + S - x) into the embedding columns of dX0 (interaction.py:26-39)
         emb_x = self.X0[:, self.nd_pad :]
@@ -302,6 +349,7 @@ class DeepFMEngine:
                      self.beta2, self.eps, op.bias_corr1, op.bias_corr2, l2s, st)
             else:
                 call("hrb_sgd_step", pp(self.params), pp(self.grads), length, self.lr, l2s, st)
+        self._refresh_wt()
         self._mark("dense_optimizer")
 
     _dws: Optional[torch.Tensor] = None

@@ -51,7 +51,7 @@ def _oracle_step(eng, tables, fields, ids, dense, label, B, hidden):
     return leaf, p, fm_w, fm_w0, logit, loss
 
 
-@pytest.mark.parametrize("B,D,n_dense,hidden,seq,dense_int", [(33, 8, 3, (8, 1), True, False), (257, 16, 13, (32, 16, 1), False, False), (64, 8, 1, (4, 1), True, True)])
+@pytest.mark.parametrize("B,D,n_dense,hidden,seq,dense_int", [(1024, 8, 3, (32, 16, 1), True, False), (2048, 16, 13, (64, 8, 1), False, False), (33, 8, 3, (8, 1), True, False), (257, 16, 13, (32, 16, 1), False, False), (64, 8, 1, (4, 1), True, True)])
 def test_engine_sgd_step_matches_oracle(dev, B, D, n_dense, hidden, seq, dense_int):
     eng, tables, fields, ids, dense, label = _setup(dev, B, D, n_dense, hidden, "sgd", seq, dense_int)
     leaf, p, fm_w, fm_w0, logit, loss = _oracle_step(eng, tables, fields, ids, dense, label, B, hidden)

@@ -7,15 +7,17 @@
 // operand tile is split in shared memory into hi = x & 0xFFFFE000 (exactly representable in TF32) and
 // lo = x - hi, and three MMAs accumulate hi*hi + lo*hi + hi*lo in TMEM (fp32): error ~2^-21, like FFMA.
 //
-// Persistent, warp-specialised (384 threads, 1 CTA/SM):
+// Persistent, warp-specialised (512 threads, 1 CTA/SM):
 //   warp 0      TMA producer   cp.async.bulk.tensor.2d (SWIZZLE_128B boxes of 32 fp32 = 128 B x rows)
 //   warp 1      MMA issuer     tcgen05.mma.cta_group::1.kind::tf32, 3 x (BK/8) instructions per k-block
 //   warp 2      TMEM allocator (2 accumulator stages x BN columns)
-//   warps 4-7   epilogue       tcgen05.ld 32x32b.x32 -> bias/activation/activation-gradient -> global
-//                              (row-major C and, optionally, the transposed copy Ct for the next bwd_w)
-//   warps 8-11  converters     hi/lo split of each landed stage, in place, fence.proxy.async
+//   warps 4-7   epilogue       tcgen05.ld 32x32b.x32 -> bias/activation/activation-gradient -> swizzled smem
+//                              staging -> TMA stores (cp.async.bulk.tensor, full 128-byte lines, OOB clipped):
+//                              row-major C and, optionally, the transposed copy Ct for the next bwd_w
+//   warps 8-15  converters     hi/lo split of each landed stage, in place, fence.proxy.async
 // Pipelines: full (TMA->conv), conv (conv->MMA), empty (MMA->TMA, tcgen05.commit), tmem_full / tmem_empty.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -25,8 +27,10 @@ namespace tc {
 constexpr int BM = 128;
 constexpr int BK = 32;  // 32 fp32 = 128 bytes = one SWIZZLE_128B span
 constexpr int STAGES = 3;
-constexpr int THREADS = 384;
+constexpr int THREADS = 512;
 constexpr int EPI_WARP0 = 4, CONV_WARP0 = 8;
+constexpr int CONV_THREADS = 256;
+constexpr uint32_t STAGE_C_BYTES = 128 * 32 * 4;  // one 128 x 32 fp32 output sub-tile
 
 enum { EPI_BIAS_ACT = 0, EPI_ACT_GRAD = 1, EPI_PLAIN = 2 };
 
@@ -63,6 +67,16 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, u
       "l"(map), "r"(s32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(map), "r"(s32(src)), "r"(c0),
+               "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(s32(src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d),
@@ -98,16 +112,20 @@ struct Args {
   int32_t act;
   int32_t splits;      // split over K (EPI_PLAIN): slice z writes C + z*M*ldc
   int32_t kb_per_split;
+  int32_t debug;       // HRB_TC_DEBUG bit mask (perf experiments only): 1 no stores, 2 no conversion, 4 no MMA, 8 no TMA
 };
 
 template <int BN, int EPI>
 __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a,
-                                                             const __grid_constant__ CUtensorMap map_b, Args g) {
+                                                             const __grid_constant__ CUtensorMap map_b,
+                                                             const __grid_constant__ CUtensorMap map_c,
+                                                             const __grid_constant__ CUtensorMap map_ct, Args g) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   constexpr uint32_t A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4;
   constexpr uint32_t STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;  // A_hi | A_lo | B_hi | B_lo
   // 1024-byte alignment of every tile (SWIZZLE_128B atoms are 8 rows x 128 B)
-  unsigned char* tiles = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // (pointer arithmetic on the __shared__ array keeps the address space known: LDS/STS, not generic LD/ST)
+  unsigned char* tiles = smem_raw + ((1024u - (s32(smem_raw) & 1023u)) & 1023u);
   __shared__ __align__(8) uint64_t full_bar[STAGES], conv_bar[STAGES], empty_bar[STAGES], tfull_bar[2], tempty_bar[2];
   __shared__ uint32_t tmem_base_smem;
 
@@ -119,7 +137,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&conv_bar[s], 128);
+      mbar_init(&conv_bar[s], CONV_THREADS);
       mbar_init(&empty_bar[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
@@ -158,6 +176,10 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
           const int s = it % STAGES;
           mbar_wait(&empty_bar[s], ((it / STAGES) & 1) ^ 1);
           unsigned char* st = tiles + (size_t)s * STAGE_BYTES;
+          if (g.debug & 8) {
+            mbar_arrive(&full_bar[s]);
+            continue;
+          }
           mbar_expect_tx(&full_bar[s], A_BYTES + B_BYTES);
           tma_load_2d(st, &map_a, &full_bar[s], kb * BK, mt * BM);
           tma_load_2d(st + 2 * A_BYTES, &map_b, &full_bar[s], kb * BK, nt * BN);
@@ -186,6 +208,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
           unsigned char* st = tiles + (size_t)s * STAGE_BYTES;
           const uint64_t a_hi = make_desc(st), a_lo = make_desc(st + A_BYTES);
           const uint64_t b_hi = make_desc(st + 2 * A_BYTES), b_lo = make_desc(st + 2 * A_BYTES + B_BYTES);
+          if (!(g.debug & 4))
 #pragma unroll
           for (int kk = 0; kk < BK / 8; ++kk) {  // UMMA_K = 8 tf32 = 32 bytes: +2 in the (>>4) start-address field
             const uint64_t o = (uint64_t)(kk * 2);
@@ -200,7 +223,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
     }
   } else if (warp >= CONV_WARP0) {
     // ===================== converters: hi/lo split in place =====================
-    const int t = threadIdx.x - CONV_WARP0 * 32;  // 0..127
+    const int t = threadIdx.x - CONV_WARP0 * 32;  // 0..255
     uint32_t it = 0;
     for (int64_t w = blockIdx.x; w < n_work; w += gridDim.x) {
       int mt, nt, z;
@@ -211,8 +234,9 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
         mbar_wait(&full_bar[s], (it / STAGES) & 1);
         unsigned char* st = tiles + (size_t)s * STAGE_BYTES;
         // element-wise, so the swizzled placement is irrelevant: lo lands at the same offset as hi
+        if (!(g.debug & 2))
 #pragma unroll 4
-        for (int i = t; i < (int)(A_BYTES / 16); i += 128) {
+        for (int i = t; i < (int)(A_BYTES / 16); i += CONV_THREADS) {
           float4* p = reinterpret_cast<float4*>(st) + i;
           float4 x = *p, h;
           h.x = __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u);
@@ -222,8 +246,9 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
           *p = h;
           reinterpret_cast<float4*>(st + A_BYTES)[i] = make_float4(x.x - h.x, x.y - h.y, x.z - h.z, x.w - h.w);
         }
+        if (!(g.debug & 2))
 #pragma unroll 4
-        for (int i = t; i < (int)(B_BYTES / 16); i += 128) {
+        for (int i = t; i < (int)(B_BYTES / 16); i += CONV_THREADS) {
           float4* p = reinterpret_cast<float4*>(st + 2 * A_BYTES) + i;
           float4 x = *p, h;
           h.x = __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u);
@@ -240,6 +265,9 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
   } else if (warp >= EPI_WARP0 && warp < EPI_WARP0 + 4) {
     // ===================== epilogue =====================
     const int q = warp - EPI_WARP0;  // == warp % 4: the TMEM lane quadrant this warp may read
+    const int et = q * 32 + lane;    // row of the 128-row tile owned by this thread
+    float* sC = reinterpret_cast<float*>(tiles + (size_t)STAGES * STAGE_BYTES);  // [128][32] fp32, SWIZZLE_128B rows
+    float* sCt = sC + STAGE_C_BYTES / 4;                                          // [32][128] fp32, plain
     uint32_t tcount = 0;
     for (int64_t w = blockIdx.x; w < n_work; w += gridDim.x, ++tcount) {
       int mt, nt, z;
@@ -247,9 +275,8 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
       const int a = tcount & 1;
       mbar_wait(&tfull_bar[a], (tcount >> 1) & 1);
       tc_fence_after();
-      const int64_t m = (int64_t)mt * BM + q * 32 + lane;
+      const int64_t m = (int64_t)mt * BM + et;
       const bool row_ok = m < g.M;
-      float* crow = g.C + (int64_t)z * g.M * g.ldc + m * g.ldc;
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
         uint32_t r[32];
@@ -264,51 +291,67 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
             : "r"(taddr));
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         const int n0 = nt * BN + c0;
-        if (n0 < g.N) {
-          float v[32];
+        if (n0 >= g.N || (g.debug & 1)) continue;  // uniform: the whole sub-tile is outside the matrix
+        float v[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-          if (row_ok) {
-            if (EPI == EPI_BIAS_ACT) {
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        if (EPI == EPI_BIAS_ACT) {
+          if (g.bias != nullptr) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (n0 + j < g.N) v[j] = act_apply(g.act, v[j] + (g.bias != nullptr ? __ldg(g.bias + n0 + j) : 0.f));
-            } else if (EPI == EPI_ACT_GRAD) {
-              if (g.aprev != nullptr) {
-                const float* ap = g.aprev + m * g.ldap + n0;
+            for (int j = 0; j < 32; ++j) v[j] += (n0 + j < g.N) ? __ldg(g.bias + n0 + j) : 0.f;
+          }
+          if (g.act == HRB_ACT_RELU) {
 #pragma unroll
-                for (int j4 = 0; j4 < 32; j4 += 4) {
-                  if (n0 + j4 + 3 < g.N) {
-                    const float4 y = __ldg(reinterpret_cast<const float4*>(ap + j4));
-                    v[j4] *= act_grad_from_out(g.act, y.x); v[j4 + 1] *= act_grad_from_out(g.act, y.y);
-                    v[j4 + 2] *= act_grad_from_out(g.act, y.z); v[j4 + 3] *= act_grad_from_out(g.act, y.w);
-                  } else {
-                    for (int j = j4; j < j4 + 4; ++j)
-                      if (n0 + j < g.N) v[j] *= act_grad_from_out(g.act, __ldg(ap + j));
-                  }
-                }
-              }
-            }
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+          } else if (g.act != HRB_ACT_LINEAR) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = act_apply(g.act, v[j]);
+          }
+        } else if (EPI == EPI_ACT_GRAD) {
+          if (g.aprev != nullptr && row_ok) {
+            const float* ap = g.aprev + m * g.ldap + n0;
 #pragma unroll
             for (int j4 = 0; j4 < 32; j4 += 4) {
+              float4 y = make_float4(1.f, 1.f, 1.f, 1.f);
               if (n0 + j4 + 3 < g.N) {
-                *reinterpret_cast<float4*>(crow + n0 + j4) = make_float4(v[j4], v[j4 + 1], v[j4 + 2], v[j4 + 3]);
+                y = __ldg(reinterpret_cast<const float4*>(ap + j4));
               } else {
-                for (int j = j4; j < j4 + 4; ++j)
-                  if (n0 + j < g.N) crow[n0 + j] = v[j];
+                if (n0 + j4 < g.N) y.x = __ldg(ap + j4);
+                if (n0 + j4 + 1 < g.N) y.y = __ldg(ap + j4 + 1);
+                if (n0 + j4 + 2 < g.N) y.z = __ldg(ap + j4 + 2);
+              }
+              if (g.act == HRB_ACT_RELU) {
+                v[j4] = y.x > 0.f ? v[j4] : 0.f; v[j4 + 1] = y.y > 0.f ? v[j4 + 1] : 0.f;
+                v[j4 + 2] = y.z > 0.f ? v[j4 + 2] : 0.f; v[j4 + 3] = y.w > 0.f ? v[j4 + 3] : 0.f;
+              } else {
+                v[j4] *= act_grad_from_out(g.act, y.x); v[j4 + 1] *= act_grad_from_out(g.act, y.y);
+                v[j4 + 2] *= act_grad_from_out(g.act, y.z); v[j4 + 3] *= act_grad_from_out(g.act, y.w);
               }
             }
           }
-          if (g.Ct != nullptr) {  // transposed copy: for a fixed column the 32 lanes write 32 consecutive m
+        }
+        // staging buffers are free once the previous TMA stores have READ them
+        if (et == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        epi_bar();
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (row_ok && n0 + j < g.N) g.Ct[(int64_t)(n0 + j) * g.ldct + m] = v[j];
-          }
+        for (int c = 0; c < 8; ++c)  // row `et`, 16-byte chunk c lands at chunk (c ^ (et % 8)): SWIZZLE_128B
+          *reinterpret_cast<float4*>(sC + et * 32 + ((c ^ (et & 7)) << 2)) = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+        if (g.Ct != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) sCt[j * 128 + et] = v[j];
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        epi_bar();
+        if (et == 0) {
+          tma_store_3d(&map_c, sC, n0, mt * BM, z);
+          if (g.Ct != nullptr) tma_store_2d(&map_ct, sCt, mt * BM, n0);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
       }
       tc_fence_before();
       mbar_arrive(&tempty_bar[a]);
     }
+    if (et == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
   }
 
   tc_fence_before();
@@ -338,28 +381,57 @@ static EncodeTiledFn encode_fn() {
   return fn;
 }
 
-// 2-D fp32 row-major [rows][cols] with leading dim ld; box = 32 columns (128 B) x box_rows, SWIZZLE_128B
-static int make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+// 2-D fp32 row-major [rows][cols] with leading dim ld; box = box_cols x box_rows
+static int make_map2(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_cols, int box_rows,
+                     CUtensorMapSwizzle swz) {
   EncodeTiledFn fn = encode_fn();
   if (fn == nullptr) return fail(HRB_CUDA_ERROR, "cuTensorMapEncodeTiled entry point not available");
   cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t gstride[1] = {(cuuint64_t)ld * 4};
-  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(HRB_CUDA_ERROR, "cuTensorMapEncodeTiled(2d) failed with CUresult %d", (int)r);
+  return HRB_OK;
+}
+// 3-D [slices][rows][cols] output map (slices = split-K partials), box = 32 x 128 x 1, SWIZZLE_128B
+static int make_map3(CUtensorMap* map, const float* base, int64_t slices, int64_t rows, int64_t cols, int64_t ld) {
+  EncodeTiledFn fn = encode_fn();
+  if (fn == nullptr) return fail(HRB_CUDA_ERROR, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t gdim[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)slices};
+  cuuint64_t gstride[2] = {(cuuint64_t)ld * 4, (cuuint64_t)rows * (cuuint64_t)ld * 4};
+  cuuint32_t box[3] = {32, 128, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)base, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) return fail(HRB_CUDA_ERROR, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  if (r != CUDA_SUCCESS) return fail(HRB_CUDA_ERROR, "cuTensorMapEncodeTiled(3d) failed with CUresult %d", (int)r);
   return HRB_OK;
 }
 
 template <int BN, int EPI>
-static int launch(const float* A, int64_t lda, const float* Bt, int64_t ldb, const Args& g, cudaStream_t st) {
-  CUtensorMap ma, mb;
-  int rc = make_map(&ma, A, g.M, g.K, lda, BM);
+static int launch(const float* A, int64_t lda, const float* Bt, int64_t ldb, const Args& g_in, cudaStream_t st) {
+  Args g = g_in;
+  static int dbg = -1;
+  if (dbg < 0) {
+    const char* e = getenv("HRB_TC_DEBUG");
+    dbg = e ? atoi(e) : 0;
+  }
+  g.debug = dbg;
+  CUtensorMap ma, mb, mc, mct;
+  int rc = make_map2(&ma, A, g.M, g.K, lda, BK, BM, CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc != HRB_OK) return rc;
-  rc = make_map(&mb, Bt, g.N, g.K, ldb, BN);
+  rc = make_map2(&mb, Bt, g.N, g.K, ldb, BK, BN, CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc != HRB_OK) return rc;
-  constexpr size_t smem = (size_t)STAGES * (2 * BM * BK * 4 + 2 * BN * BK * 4) + 1024;
+  rc = make_map3(&mc, g.C, g.splits, g.M, g.N, g.ldc);
+  if (rc != HRB_OK) return rc;
+  if (g.Ct != nullptr) {
+    rc = make_map2(&mct, g.Ct, g.N, g.M, g.ldct, 128, 32, CU_TENSOR_MAP_SWIZZLE_NONE);
+    if (rc != HRB_OK) return rc;
+  } else {
+    mct = mc;
+  }
+  constexpr size_t smem = (size_t)STAGES * (2 * BM * BK * 4 + 2 * BN * BK * 4) + 2 * STAGE_C_BYTES + 1024;
   static bool attr_done = false;
   if (!attr_done) {
     HRB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -367,7 +439,7 @@ static int launch(const float* A, int64_t lda, const float* Bt, int64_t ldb, con
   }
   const int64_t work = (int64_t)((g.M + BM - 1) / BM) * ((g.N + BN - 1) / BN) * g.splits;
   int64_t grid = work < sm_count() ? work : sm_count();
-  gemm_tc_kernel<BN, EPI><<<(unsigned)grid, THREADS, smem, st>>>(ma, mb, g);
+  gemm_tc_kernel<BN, EPI><<<(unsigned)grid, THREADS, smem, st>>>(ma, mb, mc, mct, g);
   HRB_LAUNCH_CHECK();
   return HRB_OK;
 }
@@ -386,7 +458,7 @@ using namespace hrb;
 // C[M,N] = act(A[M,K] * Bt[N,K]^T + bias)  (+ transposed copy Ct[N,M])
 int hrb_tc_gemm_bias_act(const float* a, int64_t lda, const float* bt, int64_t ldb, const float* bias, int64_t M, int32_t N, int32_t K,
                          int32_t act, float* c, int64_t ldc, float* ct, int64_t ldct, cudaStream_t st) {
-  if (!tc::tc_ok(a, lda, bt, ldb, M, N, K) || !aligned16(c) || ldc % 4 != 0)
+  if (!tc::tc_ok(a, lda, bt, ldb, M, N, K) || !aligned16(c) || ldc % 4 != 0 || (ct != nullptr && (!aligned16(ct) || ldct % 4 != 0)))
     return fail(HRB_UNSUPPORTED, "tcgen05 GEMM: shape/alignment not covered");
   tc::Args g{c, ct, bias, nullptr, ldc, ldct, 0, M, N, K, act, 1, (K + tc::BK - 1) / tc::BK};
   return tc::launch<128, tc::EPI_BIAS_ACT>(a, lda, bt, ldb, g, st);
@@ -394,7 +466,8 @@ int hrb_tc_gemm_bias_act(const float* a, int64_t lda, const float* bt, int64_t l
 // C[M,N] = (A[M,K] * Bt[N,K]^T) * act'(aprev[M,N])  (+ transposed copy)
 int hrb_tc_gemm_act_grad(const float* a, int64_t lda, const float* bt, int64_t ldb, int64_t M, int32_t N, int32_t K, const float* aprev,
                          int64_t ldap, int32_t act, float* c, int64_t ldc, float* ct, int64_t ldct, cudaStream_t st) {
-  if (!tc::tc_ok(a, lda, bt, ldb, M, N, K) || !aligned16(c) || ldc % 4 != 0 || (aprev != nullptr && (!aligned16(aprev) || ldap % 4 != 0)))
+  if (!tc::tc_ok(a, lda, bt, ldb, M, N, K) || !aligned16(c) || ldc % 4 != 0 || (aprev != nullptr && (!aligned16(aprev) || ldap % 4 != 0)) ||
+      (ct != nullptr && (!aligned16(ct) || ldct % 4 != 0)))
     return fail(HRB_UNSUPPORTED, "tcgen05 GEMM: shape/alignment not covered");
   tc::Args g{c, ct, nullptr, aprev, ldc, ldct, ldap, M, N, K, act, 1, (K + tc::BK - 1) / tc::BK};
   return tc::launch<128, tc::EPI_ACT_GRAD>(a, lda, bt, ldb, g, st);

@@ -217,6 +217,94 @@ __global__ void __launch_bounds__(256) act_bwd_kernel(const float* __restrict__ 
     dz[i] = dy[i] * act_grad_from_out(act, y[i]);
 }
 
+// ---- the 1-unit logit layer (DeepFM.py:59-60 forces units[-1] == 1): GEMV forward, fused backward ----------
+// y[m] = x[m,:] . w + b ; one warp per row, float4 loads
+__global__ void __launch_bounds__(256) dense1_fwd_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ w,
+                                                        const float* __restrict__ bias, int64_t M, int32_t K, float* __restrict__ y) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const float b0 = bias != nullptr ? __ldg(bias) : 0.f;
+  for (int64_t m = warp0; m < M; m += nwarps) {
+    const float* xr = x + m * ldx;
+    float acc = 0.f;
+    for (int k = lane * 4; k < K; k += 128) {
+      if (k + 3 < K) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(xr + k));
+        const float4 b = __ldg(reinterpret_cast<const float4*>(w + k));
+        acc = fmaf(a.x, b.x, acc); acc = fmaf(a.y, b.y, acc); acc = fmaf(a.z, b.z, acc); acc = fmaf(a.w, b.w, acc);
+      } else {
+        for (int j = k; j < K; ++j) acc = fmaf(__ldg(xr + j), __ldg(w + j), acc);
+      }
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) y[m] = acc + b0;
+  }
+}
+
+// dz_prev[m,k] = dy[m] * w[k] * act'(x[m,k]) (+ transposed copy), dw[k] += sum_m x[m,k]*dy[m], db += sum_m dy[m]
+// CTA = 32 rows x K columns per pass; per-CTA partial sums go to `part` ([grid][K+1]) for a fixed-order reduce.
+__global__ void __launch_bounds__(256) dense1_bwd_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ w,
+                                                        const float* __restrict__ dy, int64_t M, int32_t K, int32_t act,
+                                                        float* __restrict__ dzp, int64_t lddz, float* __restrict__ dzt, int64_t lddzt,
+                                                        float* __restrict__ part) {
+  extern __shared__ float sm[];
+  __shared__ float tile[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 columns x 8 rows per step
+  float* colacc = sm;                                       // [8][K+1] per-row-lane partials
+  for (int i = threadIdx.x; i < 8 * (K + 1); i += 256) colacc[i] = 0.f;
+  __syncthreads();
+  const int64_t rows_per_block = (M + gridDim.x - 1) / gridDim.x;
+  const int64_t r0 = blockIdx.x * rows_per_block, r1 = min(M, r0 + rows_per_block);
+  float dbacc = 0.f;
+  for (int64_t rb = r0; rb < r1; rb += 32) {
+    for (int kc = 0; kc < K; kc += 32) {
+      const int k = kc + tx;
+      const float wk = k < K ? __ldg(w + k) : 0.f;
+      float dwk = 0.f;
+      float t[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int64_t m = rb + ty + 8 * i;
+        t[i] = 0.f;
+        if (m < r1 && k < K) {
+          const float xv = __ldg(x + m * ldx + k);
+          const float g = __ldg(dy + m);
+          dwk = fmaf(xv, g, dwk);
+          t[i] = g * wk * act_grad_from_out(act, xv);
+          dzp[m * lddz + k] = t[i];
+        }
+      }
+      if (k < K) colacc[ty * (K + 1) + k] += dwk;
+      if (dzt != nullptr) {  // 32x32 tile transpose through shared memory: lanes run along m for the store
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) tile[ty + 8 * i][tx] = t[i];
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int kk = kc + ty + 8 * i;
+          const int64_t m = rb + tx;
+          if (kk < K && m < r1) dzt[(int64_t)kk * lddzt + m] = tile[tx][ty + 8 * i];
+        }
+      }
+    }
+    if (threadIdx.x < 32) {
+      const int64_t m = rb + threadIdx.x;
+      if (m < r1) dbacc += __ldg(dy + m);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) dbacc = warp_sum(dbacc);
+  for (int k = threadIdx.x; k < K; k += 256) {
+    float s0 = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s0 += colacc[j * (K + 1) + k];
+    part[(int64_t)blockIdx.x * (K + 1) + k] = s0;
+  }
+  if (threadIdx.x == 0) part[(int64_t)blockIdx.x * (K + 1) + K] = dbacc;
+}
+
 static inline bool vec_ok(const void* p, int64_t ld) { return aligned16(p) && ld % 4 == 0; }
 
 static int pick_splits(int64_t M, int32_t K, int32_t N) {
@@ -440,6 +528,52 @@ HRB_API int hrb_dense_bwd_w_t(const float* xt, int64_t ldxt, const float* dzt, i
     colsum_partial_kernel<<<grid, 256, 0, st>>>(dz, lddz, M, N, rpb, colpart);
     HRB_LAUNCH_CHECK();
     split_reduce_kernel<<<(N + 255) / 256, 256, 0, st>>>(colpart, 1, N, N, yb, dbias, N);
+    HRB_LAUNCH_CHECK();
+  }
+  return HRB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// 1-unit Dense layer (the DeepFM logit layer): GEMV forward and a fused backward
+// ---------------------------------------------------------------------------------------------
+HRB_API int hrb_dense1_fwd(const float* x, int64_t ldx, const float* w, const float* bias, int64_t M, int32_t K, float* y, void* stream) {
+  HRB_REQUIRE(M >= 0 && K > 0 && ldx >= K, "hrb_dense1_fwd: bad sizes");
+  if (M == 0) return HRB_OK;
+  HRB_REQUIRE(x && w && y, "hrb_dense1_fwd: null pointer");
+  HRB_REQUIRE(aligned16(x) && aligned16(w) && ldx % 4 == 0, "hrb_dense1_fwd: x/w must be 16-byte aligned, ldx %% 4 == 0");
+  const int64_t blocks = min((int64_t)sm_count() * 8, (M + 7) / 8);
+  dense1_fwd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, ldx, w, bias, M, K, y);
+  HRB_LAUNCH_CHECK();
+  return HRB_OK;
+}
+
+HRB_API int hrb_dense1_bwd_workspace(int64_t M, int32_t K, size_t* bytes) {
+  HRB_REQUIRE(bytes && M >= 0 && K > 0, "hrb_dense1_bwd_workspace: bad argument");
+  *bytes = (size_t)sm_count() * 8 * (K + 1) * sizeof(float) + 256;
+  return HRB_OK;
+}
+
+// dz_prev[M,K] = dy[M] (x) w[K] * act'(x) (+ dz_prev^T), dw[K] = x^T dy, dbias = sum dy
+HRB_API int hrb_dense1_bwd(const float* x, int64_t ldx, const float* w, const float* dy, int64_t M, int32_t K, int32_t act_prev,
+                           float* dz_prev, int64_t lddz, float* dz_prev_t, int64_t lddzt, float* dw, float* dbias, void* workspace,
+                           size_t workspace_bytes, void* stream) {
+  HRB_REQUIRE(x && w && dy && dz_prev && dw && workspace && M > 0 && K > 0 && ldx >= K && lddz >= K, "hrb_dense1_bwd: bad argument");
+  HRB_REQUIRE(dz_prev_t == nullptr || lddzt >= M, "hrb_dense1_bwd: lddzt < M");
+  size_t need = 0;
+  hrb_dense1_bwd_workspace(M, K, &need);
+  if (workspace_bytes < need) return fail(HRB_WORKSPACE, "hrb_dense1_bwd: workspace %zu < required %zu bytes", workspace_bytes, need);
+  const size_t smem = (size_t)8 * (K + 1) * sizeof(float);
+  if (smem > 48 * 1024) return fail(HRB_UNSUPPORTED, "hrb_dense1_bwd: K=%d too wide", K);
+  cudaStream_t st = (cudaStream_t)stream;
+  int grid = sm_count() * 8;  // 32-row slabs; enough CTAs to keep the loads of many slabs in flight
+  if ((int64_t)grid * 32 > M) grid = (int)((M + 31) / 32);
+  float* part = (float*)workspace;
+  dense1_bwd_kernel<<<grid, 256, smem, st>>>(x, ldx, w, dy, M, K, act_prev, dz_prev, lddz, dz_prev_t, lddzt, part);
+  HRB_LAUNCH_CHECK();
+  split_reduce_kernel<<<(K + 255) / 256, 256, 0, st>>>(part, 1, K, K + 1, grid, dw, K);
+  HRB_LAUNCH_CHECK();
+  if (dbias != nullptr) {
+    split_reduce_kernel<<<1, 256, 0, st>>>(part + K, 1, 1, K + 1, grid, dbias, 1);
     HRB_LAUNCH_CHECK();
   }
   return HRB_OK;

@@ -686,11 +686,27 @@ __global__ void __launch_bounds__(256) bwd_merge_kernel(int64_t n_chunks, int G,
     if (!(fl & PF_VALID) || (fl & PF_CONT)) continue;
     float4 acc = reinterpret_cast<const float4*>(partial + slot * (int64_t)(G * 4))[q];
     if (fl & PF_ROPEN) {
-      for (int64_t c = slot / 2 + 1; c < n_chunks; ++c) {
-        const uint32_t f2 = __ldg(pflag + 2 * c);
-        const float4 v = reinterpret_cast<const float4*>(partial + (2 * c) * (int64_t)(G * 4))[q];
-        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
-        if (!(f2 & PF_ROPEN)) break;
+      // hot rows span hundreds of chunks: fetch 8 head partials at a time (independent loads), add them in
+      // chunk order and stop at the first one that does not continue to the right
+      constexpr int W = 8;
+      bool open = true;
+      for (int64_t c0 = slot / 2 + 1; open && c0 < n_chunks; c0 += W) {
+        uint32_t f2[W];
+        float4 v[W];
+#pragma unroll
+        for (int u = 0; u < W; ++u) {
+          const bool in = c0 + u < n_chunks;
+          f2[u] = in ? __ldg(pflag + 2 * (c0 + u)) : 0u;
+          v[u] = in ? __ldg(reinterpret_cast<const float4*>(partial + (2 * (c0 + u)) * (int64_t)(G * 4)) + q)
+                    : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < W; ++u) {
+          if (open && c0 + u < n_chunks) {
+            acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w;
+            if (!(f2[u] & PF_ROPEN)) open = false;
+          }
+        }
       }
     }
     apply_row<MODE>(ctx, __ldg(pkey + slot), q, acc);

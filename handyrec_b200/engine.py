@@ -252,7 +252,9 @@ class DeepFMEngine:
         n = len(self.units)
         for i in range(n):
             act = self.act if i + 1 != n else "linear"  # core.py:66-69 with output_activation="linear"
-            if self.use_tc and self.tc_layer[i] and B == self.B:
+            if self.units[i] == 1 and self.layer_K[i] % 4 == 0:
+                call("hrb_dense1_fwd", K._p(x), ldx, K._p(self.W[i]), K._p(self.b[i]), B, self.layer_K[i], K._p(self.A[i]), st)
+            elif self.use_tc and self.tc_layer[i] and B == self.B:
                 call("hrb_dense_fwd_t", K._p(x), ldx, K._p(self.Wt[i]), self.layer_K[i], K._p(self.b[i]), B, self.layer_K[i], self.units[i],
                      _lib.ACT[act], K._p(self.A[i]), self.layer_ld[i], K._p(self.At[i]) if training else None, B, st)
             else:
@@ -293,6 +295,14 @@ class DeepFMEngine:
         for i in range(n - 1, -1, -1):
             x, ldx = (self.A[i - 1], self.layer_ld[i - 1]) if i > 0 else (self.X0, self.K0p)
             Kp, N = self.layer_K[i], self.units[i]
+            if N == 1 and i > 0 and Kp % 4 == 0 and Kp <= 1024:
+                call("hrb_dense1_bwd_workspace", B, Kp, ctypes.byref(need))
+                ws = self._dense_ws(need.value)
+                call("hrb_dense1_bwd", K._p(x), ldx, K._p(self.W[i]), K._p(dz), B, Kp, _lib.ACT[self.act], K._p(self.dZ[i - 1]), self.layer_ld[i - 1],
+                     K._p(self.dZt[i - 1]) if tc_step else None, B, K._p(self.dW[i]), K._p(self.db[i]), K._p(ws), ws.numel(), st)
+                dz, lddz = self.dZ[i - 1], self.layer_ld[i - 1]
+                self._mark(f"dense_bwd_{i}_logit")
+                continue
             if tc_step and self.tc_layer[i]:
                 xt = self.At[i - 1] if i > 0 else self.X0t
                 call("hrb_dense_bwd_w_t_workspace", B, Kp, N, ctypes.byref(need))

@@ -437,3 +437,26 @@ def dense_bwd_w_t(xt, dzt, dz=None, dw=None, dbias=None):
     call("hrb_dense_bwd_w_t", _p(xt), _row_major_2d(xt, "xt"), _p(dzt), _row_major_2d(dzt, "dzt"), _p(dz),
          _row_major_2d(dz, "dz") if dz is not None else 0, M, Kd, N, _p(dw), _row_major_2d(dw, "dw"), _p(dbias), _p(ws), ws.numel(), _stream())
     return dw, dbias
+
+
+def dense1_fwd(x, w, bias, out=None):
+    """The 1-unit logit layer: y (M,) = x (M,K) @ w (K,) + bias."""
+    M, Kd = x.shape
+    if out is None:
+        out = torch.empty(M, 1, device=x.device, dtype=torch.float32)
+    call("hrb_dense1_fwd", _p(x), _row_major_2d(x, "x"), _p(w), _p(bias), M, Kd, _p(out), _stream())
+    return out
+
+
+def dense1_bwd(x, w, dy, act_prev=None, want_t=False):
+    M, Kd = x.shape
+    need = ctypes.c_size_t(0)
+    call("hrb_dense1_bwd_workspace", M, Kd, ctypes.byref(need))
+    ws = torch.empty(need.value, device=x.device, dtype=torch.uint8)
+    ld = (Kd + 3) // 4 * 4
+    dz = torch.zeros(M, ld, device=x.device, dtype=torch.float32)
+    dzt = torch.zeros(ld, M, device=x.device, dtype=torch.float32) if want_t else None
+    dw = torch.empty(Kd, device=x.device, dtype=torch.float32)
+    db = torch.empty(1, device=x.device, dtype=torch.float32)
+    call("hrb_dense1_bwd", _p(x), _row_major_2d(x, "x"), _p(w), _p(dy), M, Kd, ACT[act_prev], _p(dz), ld, _p(dzt), M, _p(dw), _p(db), _p(ws), ws.numel(), _stream())
+    return dz[:, :Kd], (dzt[:Kd] if want_t else None), dw, db

@@ -199,6 +199,14 @@ int hrb_dense_bwd_w_t(const float* xt, int64_t ldxt, const float* dzt, int64_t l
                       int32_t K, int32_t N, float* dw, int64_t lddw, float* dbias, void* workspace, size_t workspace_bytes,
                       void* stream);
 
+/* The 1-unit logit layer (models/ranking/context_aware/DeepFM.py:59-60): GEMV forward y[m] = x[m,:].w + b and a fused
+ * backward dz_prev = dy (x) w * act'(x) (+ transposed copy), dw = x^T dy, dbias = sum dy (fixed-order reductions). */
+int hrb_dense1_fwd(const float* x, int64_t ldx, const float* w, const float* bias, int64_t M, int32_t K, float* y, void* stream);
+int hrb_dense1_bwd_workspace(int64_t M, int32_t K, size_t* bytes);
+int hrb_dense1_bwd(const float* x, int64_t ldx, const float* w, const float* dy, int64_t M, int32_t K, int32_t act_prev,
+                   float* dz_prev, int64_t lddz, float* dz_prev_t, int64_t lddzt, float* dw, float* dbias, void* workspace,
+                   size_t workspace_bytes, void* stream);
+
 /* dz = dy * act'(y) in place-capable elementwise (used at the head of a backward chain) */
 int hrb_act_bwd(const float* y, const float* dy, int64_t n, int32_t act, float* dz, void* stream);
 

@@ -81,3 +81,32 @@ def test_transpose_odd_shapes(dev):
     for r, c in ((1, 1), (33, 65), (1000, 13), (5, 432)):
         x = rnd(r, c, seed=r)
         assert torch.equal(k.transpose(x.to(dev)).cpu(), x.t().contiguous())
+
+
+@pytest.mark.parametrize("M,Kd,act", [(65536, 128, "relu"), (1000, 36, "sigmoid"), (33, 8, None), (4096, 130, "relu")])
+def test_dense1_logit_layer(dev, M, Kd, act):
+    k = K()
+    ld = (Kd + 3) // 4 * 4
+    xa = oracle.activation(act, rnd(M, Kd, seed=1)).requires_grad_(False)
+    xbuf = torch.zeros(M, ld)
+    xbuf[:, :Kd] = xa
+    w = rnd(Kd, seed=2) / np.sqrt(Kd)
+    b = torch.tensor([0.3])
+    dy = rnd(M, seed=3)
+    xd = xbuf.to(dev)
+    wd = torch.zeros(ld, device=dev)
+    wd[:Kd] = w.to(dev)
+    y = k.dense1_fwd(xd[:, :Kd], wd, b.to(dev))
+    close(y[:, 0], (xa.double() @ w.double() + 0.3).float(), 1e-5)
+    dz, dzt, dw, db = k.dense1_bwd(xd[:, :Kd], wd, dy.to(dev), act_prev=act, want_t=True)
+    if act == "relu":
+        g = (xa > 0).double()
+    elif act == "sigmoid":
+        g = (xa * (1 - xa)).double()
+    else:
+        g = torch.ones_like(xa).double()
+    want = dy.double()[:, None] * w.double()[None, :] * g
+    close(dz, want.float(), 1e-4)
+    close(dzt, want.float().t(), 1e-4)
+    close(dw, (xa.double().T @ dy.double()).float(), 1e-4)
+    close(db, dy.double().sum().float().reshape(1), 1e-4)

@@ -1136,3 +1136,297 @@ HRB_API int hrb_lookup_combine(const hrb_plan* plan, const float* psum, const fl
   HRB_LAUNCH_CHECK();
   return HRB_OK;
 }
+
+// =============================================================================================
+// (e) compact row exchange for row-sharded tables: owner(r) = r % N, local row r / N.
+//   requester: route (owner, owner-side key per position) -> sort by owner -> keys in send order
+//   owner:     rows by key (forward) / keyed sorted-segment update (backward)
+//   requester: scatter the received rows (forward) / gather the per-position gradients (backward)
+// All NCCL calls are made by the host between these kernels (handyrec_b200/sharded.py).
+// =============================================================================================
+namespace hrb {
+
+// one thread per (sample, position column): owner rank and the key in the OWNER's shard key space
+__global__ void __launch_bounds__(256) route_kernel(const FieldDev* __restrict__ fields, const int32_t* __restrict__ pos_field,
+                                                   int32_t pos_cols, const int32_t* __restrict__ ids, int64_t ids_ld, int64_t batch,
+                                                   int32_t n_ranks, const uint32_t* __restrict__ key_base /* [n_ranks][n_tables] */,
+                                                   int32_t n_tables, uint32_t* __restrict__ owner, uint32_t* __restrict__ key,
+                                                   uint32_t* __restrict__ pos) {
+  const int64_t total = batch * pos_cols;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = i / pos_cols;
+    const int c = (int)(i - b * pos_cols);
+    const FieldDev& f = fields[pos_field[c]];
+    const int32_t id = ids[b * ids_ld + f.ids_col + (c - f.pos_col)];
+    const bool valid = (f.pool == HRB_POOL_NONE || id != 0) && id >= 0;
+    const uint32_t o = valid ? (uint32_t)(id % n_ranks) : (uint32_t)n_ranks;  // n_ranks = "nobody": sorts last
+    owner[i] = o;
+    key[i] = valid ? key_base[o * n_tables + f.table_idx] + (uint32_t)(id / n_ranks) : 0xFFFFFFFFu;
+    pos[i] = (uint32_t)i;
+  }
+}
+
+// counts[r] = number of sorted owners equal to r (r in [0, n_ranks]); one thread per rank, binary search
+__global__ void owner_counts_kernel(const uint32_t* __restrict__ sorted_owner, int64_t n, int32_t n_ranks,
+                                    int64_t* __restrict__ counts) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r > n_ranks) return;
+  auto lower = [&](uint32_t v) {
+    int64_t lo = 0, hi = n;
+    while (lo < hi) {
+      const int64_t mid = (lo + hi) >> 1;
+      if (sorted_owner[mid] < v) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+  };
+  counts[r] = lower((uint32_t)r + 1) - lower((uint32_t)r);
+}
+
+__global__ void __launch_bounds__(256) gather_u32_kernel(const uint32_t* __restrict__ src, const uint32_t* __restrict__ perm,
+                                                        int64_t n, uint32_t* __restrict__ dst) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    dst[i] = src[perm[i]];
+}
+
+// owner side: out[j, :] = shard row addressed by keys[j]
+__global__ void __launch_bounds__(256) rows_by_key_kernel(const TableDev* __restrict__ tables, int32_t n_tables, int32_t chunks,
+                                                         const uint32_t* __restrict__ keys, int64_t n, float* __restrict__ out) {
+  const int64_t total = n * chunks;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t j = i / chunks;
+    const int q = (int)(i - j * chunks);
+    const uint32_t k = __ldg(keys + j);
+    const int ti = find_table(tables, n_tables, k);
+    const TableDev& t = tables[ti];
+    const int64_t row = (int64_t)(k - t.key_base);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (row < t.rows && q * 4 < t.dim) v = ldg_nc_na(reinterpret_cast<const float4*>(t.w) + row * (t.dim >> 2) + q);
+    stg_na(reinterpret_cast<float4*>(out) + i, v);
+  }
+}
+
+// requester side, forward: received row j belongs to position perm[j]; plain features go straight to the output
+// block, positions of pooled features go to the position-ordered buffer for pool_positions_kernel
+__global__ void __launch_bounds__(256) scatter_rows_kernel(const FieldDev* __restrict__ fields, const int32_t* __restrict__ pos_field,
+                                                          int32_t pos_cols, int32_t chunks, const uint32_t* __restrict__ perm,
+                                                          int64_t n, const float* __restrict__ rows, float* __restrict__ out,
+                                                          int64_t out_ld, float* __restrict__ pos_rows) {
+  const int64_t total = n * chunks;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t j = i / chunks;
+    const int q = (int)(i - j * chunks);
+    const uint32_t p = __ldg(perm + j);
+    const int64_t b = p / (uint32_t)pos_cols;
+    const int c = (int)(p - (uint32_t)b * (uint32_t)pos_cols);
+    const FieldDev& f = fields[__ldg(pos_field + c)];
+    const float4 v = __ldg(reinterpret_cast<const float4*>(rows) + i);
+    if (f.pool == HRB_POOL_NONE)
+      *(reinterpret_cast<float4*>(out + b * out_ld + f.out_col) + q) = v;
+    else
+      *(reinterpret_cast<float4*>(pos_rows) + (int64_t)p * chunks + q) = v;
+  }
+}
+
+// pooled features from the position-ordered rows (same arithmetic as pooled_chunk)
+__global__ void __launch_bounds__(256) pool_positions_kernel(const FieldDev* __restrict__ fields, int32_t n_fields, int32_t pos_cols,
+                                                            int32_t chunks, const int32_t* __restrict__ ids, int64_t ids_ld,
+                                                            int64_t batch, const float* __restrict__ pos_rows,
+                                                            float* __restrict__ out, int64_t out_ld) {
+  const int64_t total = batch * n_fields * chunks;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int q = (int)(i % chunks);
+    const int64_t bf = i / chunks;
+    const int fi = (int)(bf % n_fields);
+    const int64_t b = bf / n_fields;
+    const FieldDev& f = fields[fi];
+    if (f.pool == HRB_POOL_NONE) continue;
+    const int32_t* idp = ids + b * ids_ld + f.ids_col;
+    const float4* pr = reinterpret_cast<const float4*>(pos_rows) + (b * pos_cols + f.pos_col) * (int64_t)chunks + q;
+    float4 acc = f.pool == HRB_POOL_MAX ? make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float cnt = 0.f;
+    for (int l = 0; l < f.seq_len; ++l) {
+      if (idp[l] != 0) {
+        const float4 v = __ldg(pr + (int64_t)l * chunks);
+        cnt += 1.f;
+        if (f.pool == HRB_POOL_MAX) {
+          acc.x = fmaxf(acc.x, v.x); acc.y = fmaxf(acc.y, v.y); acc.z = fmaxf(acc.z, v.z); acc.w = fmaxf(acc.w, v.w);
+        } else {
+          acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+      }
+    }
+    if (f.pool == HRB_POOL_MEAN) {
+      const float w = cnt > 0.f ? __fdiv_rn(1.0f, cnt) : 0.0f;
+      acc.x *= w; acc.y *= w; acc.z *= w; acc.w *= w;
+    } else if (f.pool == HRB_POOL_MAX && cnt < (float)f.seq_len) {
+      acc.x = fmaxf(acc.x, -1e9f); acc.y = fmaxf(acc.y, -1e9f); acc.z = fmaxf(acc.z, -1e9f); acc.w = fmaxf(acc.w, -1e9f);
+    }
+    *(reinterpret_cast<float4*>(out + b * out_ld + f.out_col) + q) = acc;
+  }
+}
+
+// requester side, backward: gradient of position perm[j] = dout[b, field cols] * (1/n_valid for mean)
+__global__ void __launch_bounds__(256) gather_grads_kernel(const FieldDev* __restrict__ fields, const int32_t* __restrict__ pos_field,
+                                                          int32_t pos_cols, int32_t chunks, const int32_t* __restrict__ ids,
+                                                          int64_t ids_ld, const uint32_t* __restrict__ perm, int64_t n,
+                                                          const float* __restrict__ dout, int64_t dout_ld, float* __restrict__ send) {
+  const int64_t total = n * chunks;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t j = i / chunks;
+    const int q = (int)(i - j * chunks);
+    const uint32_t p = __ldg(perm + j);
+    const int64_t b = p / (uint32_t)pos_cols;
+    const int c = (int)(p - (uint32_t)b * (uint32_t)pos_cols);
+    const FieldDev& f = fields[__ldg(pos_field + c)];
+    float s = 1.0f;
+    if (f.pool == HRB_POOL_MEAN) {
+      const int32_t* idp = ids + b * ids_ld + f.ids_col;
+      int cnt = 0;
+      for (int l = 0; l < f.seq_len; ++l) cnt += idp[l] != 0;
+      s = cnt > 0 ? __fdiv_rn(1.0f, (float)cnt) : 0.f;
+    }
+    float4 v = __ldg(reinterpret_cast<const float4*>(dout + b * dout_ld + f.out_col) + q);
+    v.x *= s; v.y *= s; v.z *= s; v.w *= s;
+    reinterpret_cast<float4*>(send)[i] = v;
+  }
+}
+
+}  // namespace hrb
+
+static int route_ws(int64_t n, size_t* cub_bytes, size_t* total) {
+  size_t cb = 0;
+  cudaError_t e = cub::DeviceRadixSort::SortPairs(nullptr, cb, (const uint32_t*)nullptr, (uint32_t*)nullptr, (const uint32_t*)nullptr,
+                                                  (uint32_t*)nullptr, (int)(n > 0 ? n : 1), 0, 8);
+  if (e != cudaSuccess) return fail(HRB_CUDA_ERROR, "cub temp size query: %s", cudaGetErrorString(e));
+  *cub_bytes = cb;
+  *total = align_up((size_t)(n > 0 ? n : 1) * 4) * 4 + align_up(cb);
+  return HRB_OK;
+}
+
+HRB_API int hrb_route_workspace(const hrb_plan* plan, int64_t batch, size_t* bytes) {
+  HRB_REQUIRE(plan && bytes && batch >= 0, "hrb_route_workspace: bad argument");
+  size_t cb, tot;
+  int rc = route_ws(batch * plan->pos_cols, &cb, &tot);
+  if (rc != HRB_OK) return rc;
+  *bytes = tot;
+  return HRB_OK;
+}
+
+// perm[j] (positions in send order, grouped by owner), send_keys[j] (owner-side key of perm[j]),
+// counts[r] for r in [0, n_ranks] (the last entry counts padding positions, which are not sent)
+HRB_API int hrb_route_ids(const hrb_plan* plan, const int32_t* ids, int64_t ids_ld, int64_t batch, int32_t n_ranks,
+                          const uint32_t* key_base, uint32_t* perm, uint32_t* send_keys, int64_t* counts, void* workspace,
+                          size_t workspace_bytes, void* stream) {
+  HRB_REQUIRE(plan && ids && key_base && perm && send_keys && counts && workspace && batch >= 0 && n_ranks > 0 && n_ranks < 255,
+              "hrb_route_ids: bad argument");
+  const int64_t n = batch * plan->pos_cols;
+  HRB_REQUIRE(n < 0x7FFFFFFFll, "hrb_route_ids: batch*sum(seq_len) exceeds 2^31-1");
+  size_t cb, tot;
+  int rc = route_ws(n, &cb, &tot);
+  if (rc != HRB_OK) return rc;
+  if (workspace_bytes < tot) return fail(HRB_WORKSPACE, "hrb_route_ids: workspace %zu < required %zu bytes", workspace_bytes, tot);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n == 0) {
+    HRB_CUDA(cudaMemsetAsync(counts, 0, sizeof(int64_t) * (n_ranks + 1), st));
+    return HRB_OK;
+  }
+  const size_t seg = align_up((size_t)n * 4);
+  uint32_t* owner = (uint32_t*)workspace;
+  uint32_t* key = (uint32_t*)((char*)workspace + seg);
+  uint32_t* pos = (uint32_t*)((char*)workspace + 2 * seg);
+  uint32_t* owner_sorted = (uint32_t*)((char*)workspace + 3 * seg);
+  void* cub_tmp = (char*)workspace + 4 * seg;
+  route_kernel<<<grid_for(n, 256), 256, 0, st>>>(plan->d_fields, plan->d_pos_field, plan->pos_cols, ids, ids_ld, batch, n_ranks, key_base,
+                                               plan->n_tables, owner, key, pos);
+  HRB_LAUNCH_CHECK();
+  int bits = 1;
+  while ((1 << bits) <= n_ranks) ++bits;
+  HRB_CUDA(cub::DeviceRadixSort::SortPairs(cub_tmp, cb, owner, owner_sorted, pos, perm, (int)n, 0, bits, st));
+  count_launches(2);
+  owner_counts_kernel<<<1, 256, 0, st>>>(owner_sorted, n, n_ranks, counts);
+  HRB_LAUNCH_CHECK();
+  gather_u32_kernel<<<grid_for(n, 256), 256, 0, st>>>(key, perm, n, send_keys);
+  HRB_LAUNCH_CHECK();
+  return HRB_OK;
+}
+
+HRB_API int hrb_rows_by_key(const hrb_plan* plan, const uint32_t* keys, int64_t n, float* out, void* stream) {
+  HRB_REQUIRE(plan && n >= 0, "hrb_rows_by_key: bad argument");
+  if (n == 0) return HRB_OK;
+  HRB_REQUIRE(keys && out && aligned16(out), "hrb_rows_by_key: null/misaligned pointer");
+  if (!plan->uniform_dim) return fail(HRB_UNSUPPORTED, "hrb_rows_by_key: the row exchange needs one embedding dim");
+  const int chunks = plan->max_dim / 4;
+  rows_by_key_kernel<<<grid_for(n * chunks, 256), 256, 0, (cudaStream_t)stream>>>(plan->d_tables, plan->n_tables, chunks, keys, n, out);
+  HRB_LAUNCH_CHECK();
+  return HRB_OK;
+}
+
+HRB_API int hrb_scatter_rows(const hrb_plan* plan, const int32_t* ids, int64_t ids_ld, int64_t batch, const uint32_t* perm, int64_t n,
+                             const float* rows, float* out, int64_t out_ld, float* pos_rows, void* stream) {
+  HRB_REQUIRE(plan && ids && out && batch >= 0 && n >= 0, "hrb_scatter_rows: bad argument");
+  HRB_REQUIRE(aligned16(out) && out_ld % 4 == 0, "hrb_scatter_rows: out must be 16-byte aligned, out_ld %% 4 == 0");
+  if (!plan->uniform_dim) return fail(HRB_UNSUPPORTED, "hrb_scatter_rows: the row exchange needs one embedding dim");
+  HRB_REQUIRE(plan->all_len1 || pos_rows != nullptr, "hrb_scatter_rows: pooled features need the position buffer");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int chunks = plan->max_dim / 4;
+  if (n > 0) {
+    HRB_REQUIRE(perm && rows && aligned16(rows), "hrb_scatter_rows: null/misaligned pointer");
+    scatter_rows_kernel<<<grid_for(n * chunks, 256), 256, 0, st>>>(plan->d_fields, plan->d_pos_field, plan->pos_cols, chunks, perm, n, rows,
+                                                                  out, out_ld, pos_rows);
+    HRB_LAUNCH_CHECK();
+  }
+  if (!plan->all_len1 && batch > 0) {
+    pool_positions_kernel<<<grid_for(batch * plan->n_fields * chunks, 256), 256, 0, st>>>(plan->d_fields, plan->n_fields, plan->pos_cols,
+                                                                                         chunks, ids, ids_ld, batch, pos_rows, out, out_ld);
+    HRB_LAUNCH_CHECK();
+  }
+  return HRB_OK;
+}
+
+HRB_API int hrb_gather_grads(const hrb_plan* plan, const int32_t* ids, int64_t ids_ld, const uint32_t* perm, int64_t n,
+                             const float* dout, int64_t dout_ld, float* send, void* stream) {
+  HRB_REQUIRE(plan && n >= 0, "hrb_gather_grads: bad argument");
+  if (n == 0) return HRB_OK;
+  HRB_REQUIRE(ids && perm && dout && send && aligned16(dout) && aligned16(send) && dout_ld % 4 == 0, "hrb_gather_grads: null/misaligned pointer");
+  if (!plan->uniform_dim || plan->has_max) return fail(HRB_UNSUPPORTED, "hrb_gather_grads: needs one embedding dim and no max pooling");
+  const int chunks = plan->max_dim / 4;
+  gather_grads_kernel<<<grid_for(n * chunks, 256), 256, 0, (cudaStream_t)stream>>>(plan->d_fields, plan->d_pos_field, plan->pos_cols, chunks,
+                                                                                  ids, ids_ld, perm, n, dout, dout_ld, send);
+  HRB_LAUNCH_CHECK();
+  return HRB_OK;
+}
+
+HRB_API int hrb_keyed_bwd_workspace(const hrb_plan* plan, int64_t n, size_t* bytes) {
+  HRB_REQUIRE(plan && bytes && n >= 0 && n < 0x7FFFFFFFll, "hrb_keyed_bwd_workspace: bad argument");
+  BwdWorkspace w;
+  int rc = carve_bwd_ws(n > 0 ? n : 1, 1, plan->max_dim, plan->key_bits, nullptr, w);
+  if (rc != HRB_OK) return rc;
+  *bytes = w.total;
+  return HRB_OK;
+}
+
+// owner side, backward: (key, gradient row) pairs -> sort -> segment-reduce -> row update of the shard tables
+HRB_API int hrb_keyed_bwd_update(const hrb_plan* plan, const uint32_t* keys, const float* grads, int64_t n, const hrb_opt_params* opt_host,
+                                 void* workspace, size_t workspace_bytes, void* stream) {
+  HRB_REQUIRE(plan && opt_host && workspace && n >= 0 && n < 0x7FFFFFFFll, "hrb_keyed_bwd_update: bad argument");
+  if (n == 0) return HRB_OK;
+  HRB_REQUIRE(keys && grads && aligned16(grads), "hrb_keyed_bwd_update: null/misaligned pointer");
+  if (!plan->uniform_dim) return fail(HRB_UNSUPPORTED, "hrb_keyed_bwd_update: needs one embedding dim");
+  HRB_REQUIRE(opt_host->opt == HRB_OPT_SGD || opt_host->opt == HRB_OPT_ADAM_LAZY, "hrb_keyed_bwd_update: unknown optimiser %d", opt_host->opt);
+  if (opt_host->opt == HRB_OPT_ADAM_LAZY)
+    for (const auto& t : plan->tdev_host) HRB_REQUIRE(t.m && t.v, "hrb_keyed_bwd_update: lazy Adam needs adam_m/adam_v for every table");
+  BwdWorkspace w;
+  int rc = carve_bwd_ws(n, 1, plan->max_dim, plan->key_bits, workspace, w);
+  if (rc != HRB_OK) return rc;
+  if (w.total > workspace_bytes) return fail(HRB_WORKSPACE, "hrb_keyed_bwd_update: workspace %zu < required %zu bytes", workspace_bytes, w.total);
+  cudaStream_t st = (cudaStream_t)stream;
+  // keys_in = keys (anything outside the shard's key space becomes the sentinel), vals_in = 0..n-1 (gradient row index)
+  HRB_REQUIRE(plan->total_rows < 0x7FFFFFFFull, "hrb_keyed_bwd_update: shard key space exceeds 2^31");
+  flat_keys_kernel<<<grid_for(n, 256), 256, 0, st>>>(reinterpret_cast<const int32_t*>(keys), n, (int64_t)plan->total_rows,
+                                                    (uint32_t)plan->total_rows, w.keys_in, w.vals_in);
+  HRB_LAUNCH_CHECK();
+  FlatGrad src{grads, plan->max_dim};
+  ApplyCtx ctx{plan->d_tables, plan->n_tables, *opt_host, nullptr, 0.f};
+  if (opt_host->opt == HRB_OPT_ADAM_LAZY) ctx.lr_t = opt_host->lr * sqrtf(opt_host->bias_corr2) / opt_host->bias_corr1;
+  return run_sorted_update(opt_host->opt == HRB_OPT_SGD ? 0 : 1, w, n, (uint32_t)plan->total_rows, plan->key_bits, plan->max_dim / 4, src, ctx, st);
+}

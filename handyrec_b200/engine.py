@@ -245,9 +245,7 @@ class DeepFMEngine:
             call("hrb_pack_dense", K._p(dense), int(dense.dtype == torch.int32), dense.stride(0), B, self.n_dense, self.nd_pad,
                  K._p(self.X0), self.K0p, st)
             self._mark("pack_dense")
-        call("hrb_lookup_fm_fwd", self.plan._h, K._p(ids), ids.stride(0), B, K._p(self.X0), self.K0p, None, K._p(self.fm_w),
-             K._p(self.fm_w0), K._p(self.fm_out), K._p(self.fm_sum), None, st)
-        self._mark("lookup_fm_fwd")
+        self._lookup_fm_forward(ids, B, st)
         x, ldx = self.X0, self.K0p
         n = len(self.units)
         for i in range(n):
@@ -266,6 +264,22 @@ class DeepFMEngine:
             x, ldx = self.A[i], self.layer_ld[i]
         return self.A[-1]
 
+    def _lookup_fm_forward(self, ids, B, st) -> None:
+        """ids -> pooled embeddings in X0[:, nd_pad:], FM logit and field sum (overridden by the sharded engine)."""
+        call("hrb_lookup_fm_fwd", self.plan._h, K._p(ids), ids.stride(0), B, K._p(self.X0), self.K0p, None, K._p(self.fm_w),
+             K._p(self.fm_w0), K._p(self.fm_out), K._p(self.fm_sum), None, st)
+        self._mark("lookup_fm_fwd")
+
+    def _embedding_backward(self, ids, B, st, op) -> None:
+        call("hrb_lookup_bwd_update", self.plan._h, K._p(ids), ids.stride(0), B, K._p(self.dX0), self.K0p, None, ctypes.byref(op),
+             K._p(self._ws_emb), self._ws_emb.numel(), st)
+        self._mark("embedding_bwd_update")
+
+    def _sync_dense_grads(self) -> None:
+        """Replicated dense parameters: the sharded engine all-reduces the flat gradient buffer here."""
+
+    grad_scale_div = 1  # number of ranks the batch mean is taken over
+
     def predict_on_device(self, ids: torch.Tensor, dense: Optional[torch.Tensor]) -> torch.Tensor:
         B = ids.shape[0]
         self.forward(ids, dense)
@@ -280,7 +294,7 @@ class DeepFMEngine:
         self.forward(ids, dense, training=True)
         self.loss_sum.zero_()
         dlogit = self.dZ[-1]  # (B, 1): the logit layer has one unit (DeepFM.py:59-60)
-        call("hrb_sigmoid_bce", K._p(self.A[-1]), K._p(self.fm_out), K._p(label), B, 1.0 / B, K._p(self.prob), K._p(dlogit), K._p(self.loss_sum), st)
+        call("hrb_sigmoid_bce", K._p(self.A[-1]), K._p(self.fm_out), K._p(label), B, 1.0 / (B * self.grad_scale_div), K._p(self.prob), K._p(dlogit), K._p(self.loss_sum), st)
         self._mark("sigmoid_bce")
         self._backward(ids, B, st)
 
@@ -345,9 +359,8 @@ class DeepFMEngine:
         op.opt = _lib.OPT_SGD if self.emb_opt == "sgd" else _lib.OPT_ADAM_LAZY
         op.lr, op.beta1, op.beta2, op.eps, op.l2_scale = self.lr, self.beta1, self.beta2, self.eps, 2.0 * self.l2_embd
         op.bias_corr1, op.bias_corr2 = 1.0 - self.beta1 ** self.step_count, 1.0 - self.beta2 ** self.step_count
-        call("hrb_lookup_bwd_update", self.plan._h, K._p(ids), ids.stride(0), B, K._p(self.dX0), self.K0p, None, ctypes.byref(op),
-             K._p(self._ws_emb), self._ws_emb.numel(), st)
-        self._mark("embedding_bwd_update")
+        self._embedding_backward(ids, B, st, op)
+        self._sync_dense_grads()
         # dense parameters
         segs = [(0, self.n_params, False)] if self.l2_dnn == 0.0 else self._segments
         for off, length, reg in segs:

@@ -270,6 +270,27 @@ int hrb_lookup_partial_fwd(const hrb_plan* plan, const int32_t* local_ids, int64
 int hrb_lookup_combine(const hrb_plan* plan, const float* psum, const float* pcount, int32_t n_ranks,
                        int64_t batch, int64_t out_ld, float* out, float* inv_count, void* stream);
 
+/* Compact row exchange (what handyrec_b200/sharded.py runs between NCCL all-to-alls):
+ *   requester  hrb_route_ids     owner rank + owner-side key of every position, grouped by owner (stable):
+ *                                perm[j] = position (b*sum_L + column), send_keys[j], counts[0..n_ranks] (last = padding).
+ *                                key_base[r*n_tables + t] = first key of table t in rank r's shard key space.
+ *   owner      hrb_rows_by_key   out[j,:] = shard row addressed by keys[j]
+ *   requester  hrb_scatter_rows  rows -> output block (plain features) / position buffer + pooling (sequence features)
+ *   requester  hrb_gather_grads  send[j,:] = dout[b, field(perm[j]) columns] * (1/n_valid for mean pooling)
+ *   owner      hrb_keyed_bwd_update  (key, gradient row) pairs -> sort -> segment-reduce -> SGD / lazy-Adam row update */
+int hrb_route_workspace(const hrb_plan* plan, int64_t batch, size_t* bytes);
+int hrb_route_ids(const hrb_plan* plan, const int32_t* ids, int64_t ids_ld, int64_t batch, int32_t n_ranks,
+                  const uint32_t* key_base, uint32_t* perm, uint32_t* send_keys, int64_t* counts, void* workspace,
+                  size_t workspace_bytes, void* stream);
+int hrb_rows_by_key(const hrb_plan* plan, const uint32_t* keys, int64_t n, float* out, void* stream);
+int hrb_scatter_rows(const hrb_plan* plan, const int32_t* ids, int64_t ids_ld, int64_t batch, const uint32_t* perm, int64_t n,
+                     const float* rows, float* out, int64_t out_ld, float* pos_rows, void* stream);
+int hrb_gather_grads(const hrb_plan* plan, const int32_t* ids, int64_t ids_ld, const uint32_t* perm, int64_t n,
+                     const float* dout, int64_t dout_ld, float* send, void* stream);
+int hrb_keyed_bwd_workspace(const hrb_plan* plan, int64_t n, size_t* bytes);
+int hrb_keyed_bwd_update(const hrb_plan* plan, const uint32_t* keys, const float* grads, int64_t n, const hrb_opt_params* opt_host,
+                         void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -190,12 +190,23 @@ def main():
     B = args.batch
     vocabs = [max(4, int(v * args.scale_vocab)) for v in CRITEO_VOCABS]
     tables = []
-    for f, v in enumerate(vocabs):
-        t = torch.empty(v, EMB_DIM, device=dev)
-        K.init_uniform(t, seed=7 + f)
-        tables.append(t)
     fields = [(f, 1, "none") for f in range(len(vocabs))]
-    eng = DeepFMEngine(tables, fields, N_DENSE, DNN_HIDDEN, "relu", batch_size=B, optimizer=args.optimizer, lr=1e-3, l2_embd=0.0, seed=2022)
+    if world == 1:
+        for f, v in enumerate(vocabs):
+            t = torch.empty(v, EMB_DIM, device=dev)
+            K.init_uniform(t, seed=7 + f)
+            tables.append(t)
+        eng = DeepFMEngine(tables, fields, N_DENSE, DNN_HIDDEN, "relu", batch_size=B, optimizer=args.optimizer, lr=1e-3, l2_embd=0.0, seed=2022)
+    else:
+        # row-sharded tables: this rank holds rows r with r % world == rank (bit-identical to the rows of the full table)
+        from handyrec_b200.sharded import ShardedDeepFMEngine, TorchDistComm, shard_rows
+
+        for f, v in enumerate(vocabs):
+            t = torch.empty(shard_rows(v, rank, world), EMB_DIM, device=dev)
+            K.init_uniform(t, seed=7 + f, row_start=rank, row_step=world)
+            tables.append(t)
+        eng = ShardedDeepFMEngine(tables, vocabs, fields, N_DENSE, TorchDistComm(), dnn_hidden_units=DNN_HIDDEN, dnn_activation="relu",
+                                  batch_size=B, optimizer=args.optimizer, lr=1e-3, l2_embd=0.0, seed=2022)
     NB = 4  # rotating pool of distinct batches (tables are 6.5 GB >> 126 MB L2: every step touches fresh rows)
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
     ids_pool, dense_pool, label_pool = [], [], []
@@ -268,7 +279,10 @@ def main():
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
     for s in range(reps):
-        eng.plan.forward(ids_pool[s % NB], out=eng.X0, fm=(eng.fm_w, eng.fm_w0), want_fm_sum=False)
+        if world == 1:
+            eng.plan.forward(ids_pool[s % NB], out=eng.X0, fm=(eng.fm_w, eng.fm_w0), want_fm_sum=False)
+        else:
+            eng.exchange.forward(ids_pool[s % NB], eng.X0)
     b.record()
     torch.cuda.synchronize()
     lookup_alone_ms = a.elapsed_time(b) / reps
@@ -299,10 +313,11 @@ def main():
         return {"kernel": name, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
                 "peak_source": f"{peaks['source']} copy bandwidth ({peak_kind})"}
 
-    roofline = roofline_for(dom, phases[dom], "sustained") if dom in flops or dom == "lookup_fm_fwd" else {
+    lk = "lookup_fm_fwd" if world == 1 else "sharded_lookup_fwd"
+    roofline = roofline_for(dom, phases[dom], "sustained") if dom in flops or dom == lk else {
         "kernel": dom, "bound": "hbm", "achieved": None, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": None, "traffic": None}
     roofline["share_of_step"] = phases[dom] / total_phase
-    rl_lookup = roofline_for("lookup_fm_fwd", phases["lookup_fm_fwd"], "in-step")
+    rl_lookup = roofline_for(lk, phases[lk], "in-step")
     rl_lookup["alone_ms"] = lookup_alone_ms
     rl_lookup["alone_achieved"] = lookup_bytes / (lookup_alone_ms * 1e-3) / 1e9
     rl_lookup["alone_frac"] = rl_lookup["alone_achieved"] / peaks["hbm_gbs"]
@@ -320,7 +335,8 @@ def main():
         "config": {"workload": "DeepFM Criteo-shape: 26 sparse + 13 dense, emb dim 16, DNN 429-256-128-1, batch 65536/GPU (BASELINE.json configs[2])",
                    "global_batch": B * world, "tables_rows": sum(vocabs), "tables_gb": sum(vocabs) * EMB_DIM * 4 / 1e9, "ids": args.ids,
                    "optimizer": f"{args.optimizer} (dense params) + {eng.emb_opt} (touched embedding rows)", "l2_embd": 0.0,
-                   "l2_flush": "inputs larger than L2 (6.5 GB of tables, rotating pool of 4 batches)", "scale_vocab": args.scale_vocab},
+                   "l2_flush": "inputs larger than L2 (6.5 GB of tables, rotating pool of 4 batches)", "scale_vocab": args.scale_vocab,
+                   "parallelism": "single GPU" if world == 1 else f"dp{world}: batch split, tables row-sharded (row % {world}), NCCL all-to-all for keys/rows/gradient rows, all-reduce for dense grads"},
         "e2e": {"value": B * world * args.steps / (e2e_ms * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": eng.h2d_bytes_per_step(B), "d2h_bytes_per_step": 4,
                 "ms_per_step": e2e_ms / args.steps, "last_loss": loss},
         "gpu_launches": launches, "gpu_launches_per_step": launches / max(args.steps, 1),

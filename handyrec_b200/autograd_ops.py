@@ -1,0 +1,258 @@
+"""torch.autograd.Function wrappers of the C-ABI kernels (layer face).
+
+torch's autograd engine only ORDERS the backward calls; every forward and backward computation is a kernel of
+libhrb200.so.  These functions are what the Keras-like layers in handyrec_b200.layers call.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional
+
+import torch
+
+from . import _lib
+from . import kernels as K
+from ._lib import ACT, POOL, call
+
+
+class EmbeddingFn(torch.autograd.Function):
+    """layers/tools.py:87-101 forward; TF IndexedSlices gradient as a dense, sorted-segment reduction."""
+
+    @staticmethod
+    def forward(ctx, table, ids, mask_zero):
+        out, mask = K.embedding_fwd(table, ids.contiguous(), mask_zero)
+        ctx.save_for_backward(ids)
+        ctx.vocab = table.shape[0]
+        ctx.mark_non_differentiable(*( [mask] if mask is not None else []))
+        return (out, mask) if mask is not None else (out, torch.empty(0, device=table.device, dtype=torch.bool))
+
+    @staticmethod
+    def backward(ctx, dout, _dmask):
+        (ids,) = ctx.saved_tensors
+        D = dout.shape[-1]
+        return K.embedding_bwd_dense(ids.reshape(-1), dout.contiguous().reshape(-1, D), ctx.vocab), None, None
+
+
+class SeqPoolFn(torch.autograd.Function):
+    """layers/sequence.py:26-46."""
+
+    @staticmethod
+    def forward(ctx, x, mask, method):
+        x = x.contiguous()
+        out = K.seq_pool_fwd(x, mask.contiguous(), method)
+        ctx.save_for_backward(x, mask)
+        ctx.method = method
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, mask = ctx.saved_tensors
+        B, L, D = x.shape
+        return K.seq_pool_bwd(x, mask.contiguous(), dout.contiguous().reshape(B, D), ctx.method), None, None
+
+
+class FMFn(torch.autograd.Function):
+    """layers/interaction.py:26-39."""
+
+    @staticmethod
+    def forward(ctx, x, w, w0):
+        x = x.contiguous()
+        ctx.save_for_backward(x, w)
+        return K.fm_fwd(x, w.contiguous(), w0)
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, w = ctx.saved_tensors
+        dx, dw, dw0 = K.fm_bwd(x, w.contiguous(), dout.contiguous().reshape(-1))
+        return dx, dw.reshape(w.shape), dw0
+
+
+class DenseFn(torch.autograd.Function):
+    """Keras Dense on the last axis with a fused element-wise activation (layers/core.py:61-69)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, act):
+        lead = x.shape[:-1]
+        x2 = x.contiguous().reshape(-1, x.shape[-1])
+        y = K.dense_fwd(x2, w.contiguous(), b, act)
+        ctx.save_for_backward(x2, w, y)
+        ctx.act, ctx.lead, ctx.has_bias = act, lead, b is not None
+        return y.reshape(*lead, w.shape[1])
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, w, y = ctx.saved_tensors
+        dy2 = dy.contiguous().reshape(-1, w.shape[1])
+        dz = K.act_bwd(y, dy2, ctx.act) if ctx.act not in (None, "linear") else dy2
+        dx = K.dense_bwd_x(dz, w.contiguous())
+        dw, db = K.dense_bwd_w(x2, dz, want_bias=ctx.has_bias)
+        return dx.reshape(*ctx.lead, w.shape[0]), dw, (db if ctx.has_bias else None), None
+
+
+class DiceFn(torch.autograd.Function):
+    """layers/activation.py:27-42; mean/var are the layer's moving statistics (overwritten by batch statistics when training)."""
+
+    @staticmethod
+    def forward(ctx, x, alpha, mean, var, training, eps):
+        x = x.contiguous()
+        bm, bv = (torch.empty_like(mean), torch.empty_like(var)) if training else (mean, var)
+        y = K.dice_fwd(x, alpha, bm, bv, training, eps)
+        ctx.save_for_backward(x, alpha, bm, bv)
+        ctx.training, ctx.eps = training, eps
+        ctx.batch_stats = (bm, bv)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, alpha, bm, bv = ctx.saved_tensors
+        dx, dalpha = K.dice_bwd(x, dy.contiguous(), alpha, bm, bv, ctx.training, ctx.eps)
+        return dx, dalpha, None, None, None, None
+
+
+class BatchNormFn(torch.autograd.Function):
+    """Keras BatchNormalization on the last axis (layers/core.py:71-72)."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, mean, var, training, eps):
+        x = x.contiguous()
+        units = x.shape[-1]
+        rows = x.numel() // units
+        bm, bv = (torch.empty_like(mean), torch.empty_like(var)) if training else (mean, var)
+        y = torch.empty_like(x)
+        call("hrb_batchnorm_fwd", K._p(x), rows, units, K._p(gamma), K._p(beta), K._p(bm), K._p(bv), eps, int(training), K._p(y), K._stream())
+        ctx.save_for_backward(x, gamma, bm, bv)
+        ctx.training, ctx.eps = training, eps
+        ctx.batch_stats = (bm, bv)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, gamma, bm, bv = ctx.saved_tensors
+        units = x.shape[-1]
+        rows = x.numel() // units
+        dy = dy.contiguous()
+        dx = torch.empty_like(x)
+        dg, db = torch.empty_like(gamma), torch.empty_like(gamma)
+        scratch = torch.empty(2 * units, device=x.device, dtype=torch.float32)
+        call("hrb_batchnorm_bwd", K._p(x), K._p(dy), rows, units, K._p(gamma), K._p(bm), K._p(bv), ctx.eps, int(ctx.training), K._p(dx), K._p(dg),
+             K._p(db), K._p(scratch), K._stream())
+        return dx, dg, db, None, None, None, None
+
+
+class DropoutFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, rate, seed):
+        x = x.contiguous()
+        y = torch.empty_like(x)
+        call("hrb_dropout", K._p(x), x.numel(), float(rate), seed & 0xFFFFFFFF, K._p(y), K._stream())
+        ctx.rate, ctx.seed = rate, seed
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        dy = dy.contiguous()
+        dx = torch.empty_like(dy)
+        call("hrb_dropout", K._p(dy), dy.numel(), float(ctx.rate), ctx.seed & 0xFFFFFFFF, K._p(dx), K._stream())
+        return dx, None, None
+
+
+class AttInputFn(torch.autograd.Function):
+    """[q, k, q-k, q*k] (layers/sequence.py:96-97)."""
+
+    @staticmethod
+    def forward(ctx, q, k):
+        q, k = q.contiguous(), k.contiguous()
+        B, T, D = k.shape
+        out = torch.empty(B, T, 4 * D, device=k.device, dtype=torch.float32)
+        call("hrb_att_input_fwd", K._p(q), K._p(k), B, T, D, K._p(out), K._stream())
+        ctx.save_for_backward(q, k)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        q, k = ctx.saved_tensors
+        B, T, D = k.shape
+        dq, dk = torch.empty_like(q), torch.empty_like(k)
+        call("hrb_att_input_bwd", K._p(q), K._p(k), K._p(g.contiguous()), B, T, D, K._p(dq), K._p(dk), K._stream())
+        return dq, dk
+
+
+class MaskScoresFn(torch.autograd.Function):
+    """att_out * cast(mask) (layers/sequence.py:101); scores (B,T), mask (B,T) bool."""
+
+    @staticmethod
+    def forward(ctx, s, mask):
+        s = s.contiguous()
+        m = mask.contiguous().view(torch.uint8)
+        out = torch.empty_like(s)
+        call("hrb_mask_scores", K._p(s), K._p(m), s.numel(), K._p(out), K._stream())
+        ctx.save_for_backward(m)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (m,) = ctx.saved_tensors
+        g = g.contiguous()
+        out = torch.empty_like(g)
+        call("hrb_mask_scores", K._p(g), K._p(m), g.numel(), K._p(out), K._stream())
+        return out, None
+
+
+class AttPoolFn(torch.autograd.Function):
+    """tf.matmul(att (B,1,T), keys (B,T,D)) (models/ranking/sequential/DIN.py:93)."""
+
+    @staticmethod
+    def forward(ctx, s, k):
+        s, k = s.contiguous(), k.contiguous()
+        B, T, D = k.shape
+        out = torch.empty(B, 1, D, device=k.device, dtype=torch.float32)
+        call("hrb_att_pool_fwd", K._p(s), K._p(k), B, T, D, K._p(out), K._stream())
+        ctx.save_for_backward(s, k)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        s, k = ctx.saved_tensors
+        B, T, D = k.shape
+        ds, dk = torch.empty_like(s), torch.empty_like(k)
+        call("hrb_att_pool_bwd", K._p(s), K._p(k), K._p(g.contiguous()), B, T, D, K._p(ds), K._p(dk), K._stream())
+        return ds, dk
+
+
+class SigmoidBCEFn(torch.autograd.Function):
+    """mean sigmoid cross-entropy with logits (Keras binary_crossentropy on a sigmoid output uses the cached logits)."""
+
+    @staticmethod
+    def forward(ctx, logit, label):
+        logit = logit.contiguous().reshape(-1)
+        label = label.contiguous().reshape(-1).to(torch.float32)
+        B = logit.numel()
+        dl = torch.empty_like(logit)
+        ls = torch.zeros(1, device=logit.device, dtype=torch.float32)
+        K.sigmoid_bce(logit, None, label, 1.0 / B, None, dl, ls)
+        ctx.save_for_backward(dl)
+        return (ls / B).reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        (dl,) = ctx.saved_tensors
+        return (dl * g).reshape(-1, 1), None
+
+
+class ActivationFn(torch.autograd.Function):
+    """Stand-alone Keras Activation(name) for relu / sigmoid / tanh (element-wise)."""
+
+    @staticmethod
+    def forward(ctx, x, act):
+        x2 = x.contiguous().reshape(-1, 1)
+        # y = act(x * 1 + 0): the dense kernel with a 1x1 identity weight is the element-wise activation
+        one = torch.ones(1, 1, device=x.device, dtype=torch.float32)
+        y = K.dense_fwd(x2, one, None, act, mode=_lib.GEMM_FP32)
+        ctx.save_for_backward(y)
+        ctx.act = act
+        return y.reshape(x.shape)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (y,) = ctx.saved_tensors
+        return K.act_bwd(y, dy.contiguous().reshape(-1, 1), ctx.act).reshape(dy.shape), None

@@ -242,67 +242,75 @@ __global__ void __launch_bounds__(256) dense1_fwd_kernel(const float* __restrict
   }
 }
 
-// dz_prev[m,k] = dy[m] * w[k] * act'(x[m,k]) (+ transposed copy), dw[k] += sum_m x[m,k]*dy[m], db += sum_m dy[m]
-// CTA = 32 rows x K columns per pass; per-CTA partial sums go to `part` ([grid][K+1]) for a fixed-order reduce.
+// dz_prev[m,k] = dy[m] * w[k] * act'(x[m,k]) (+ transposed copy), dw[k] = sum_m x[m,k]*dy[m], db = sum_m dy[m]
+// 8 warps x 4 rows = one 32-row slab per pass; lane l owns columns l, l+32, ... (coalesced 128-byte accesses),
+// weight-gradient partials stay in registers across slabs; the transposed copy goes through a padded smem tile so
+// that its stores run along m.  Per-CTA partials land in `part` ([grid][K+1]) for a fixed-order reduce.
+constexpr int D1_MAXG = 16;  // K <= 512
 __global__ void __launch_bounds__(256) dense1_bwd_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ w,
                                                         const float* __restrict__ dy, int64_t M, int32_t K, int32_t act,
                                                         float* __restrict__ dzp, int64_t lddz, float* __restrict__ dzt, int64_t lddzt,
                                                         float* __restrict__ part) {
-  extern __shared__ float sm[];
-  __shared__ float tile[32][33];
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 columns x 8 rows per step
-  float* colacc = sm;                                       // [8][K+1] per-row-lane partials
-  for (int i = threadIdx.x; i < 8 * (K + 1); i += 256) colacc[i] = 0.f;
-  __syncthreads();
-  const int64_t rows_per_block = (M + gridDim.x - 1) / gridDim.x;
-  const int64_t r0 = blockIdx.x * rows_per_block, r1 = min(M, r0 + rows_per_block);
+  __shared__ float tile[32][129];
+  __shared__ float red[8][D1_MAXG * 32 + 1];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int groups = (K + 31) / 32;
+  float wk[D1_MAXG], dwacc[D1_MAXG];
+#pragma unroll
+  for (int j = 0; j < D1_MAXG; ++j) {
+    const int k = lane + 32 * j;
+    wk[j] = (j < groups && k < K) ? __ldg(w + k) : 0.f;
+    dwacc[j] = 0.f;
+  }
   float dbacc = 0.f;
-  for (int64_t rb = r0; rb < r1; rb += 32) {
-    for (int kc = 0; kc < K; kc += 32) {
-      const int k = kc + tx;
-      const float wk = k < K ? __ldg(w + k) : 0.f;
-      float dwk = 0.f;
-      float t[4];
+  for (int64_t row0 = (int64_t)blockIdx.x * 32; row0 < M; row0 += (int64_t)gridDim.x * 32) {
+#pragma unroll
+    for (int pass = 0; pass < D1_MAXG / 4; ++pass) {  // 128 columns per pass through the tile (unrolled: register arrays)
+      const int g0 = pass * 4;
+      if (g0 >= groups) break;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const int64_t m = rb + ty + 8 * i;
-        t[i] = 0.f;
-        if (m < r1 && k < K) {
-          const float xv = __ldg(x + m * ldx + k);
-          const float g = __ldg(dy + m);
-          dwk = fmaf(xv, g, dwk);
-          t[i] = g * wk * act_grad_from_out(act, xv);
-          dzp[m * lddz + k] = t[i];
+        const int r = warp * 4 + i;
+        const int64_t m = row0 + r;
+        const float g = m < M ? __ldg(dy + m) : 0.f;
+        if (g0 == 0 && lane == 0) dbacc += g;
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          const int j = pass * 4 + jj;
+          const int k = lane + 32 * j;
+          float t = 0.f;
+          if (j < groups && k < K && m < M) {
+            const float xv = __ldg(x + m * ldx + k);
+            dwacc[j] = fmaf(xv, g, dwacc[j]);
+            t = g * wk[j] * act_grad_from_out(act, xv);
+            dzp[m * lddz + k] = t;
+          }
+          tile[r][lane + 32 * jj] = t;
         }
       }
-      if (k < K) colacc[ty * (K + 1) + k] += dwk;
-      if (dzt != nullptr) {  // 32x32 tile transpose through shared memory: lanes run along m for the store
+      if (dzt != nullptr) {
         __syncthreads();
 #pragma unroll
-        for (int i = 0; i < 4; ++i) tile[ty + 8 * i][tx] = t[i];
-        __syncthreads();
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int kk = kc + ty + 8 * i;
-          const int64_t m = rb + tx;
-          if (kk < K && m < r1) dzt[(int64_t)kk * lddzt + m] = tile[tx][ty + 8 * i];
+        for (int c = warp * 16; c < warp * 16 + 16; ++c) {  // 128 tile columns, 16 per warp; lanes run along m
+          const int k = g0 * 32 + c;
+          const int64_t m = row0 + lane;
+          if (k < K && m < M) dzt[(int64_t)k * lddzt + m] = tile[lane][c];
         }
+        __syncthreads();
       }
-    }
-    if (threadIdx.x < 32) {
-      const int64_t m = rb + threadIdx.x;
-      if (m < r1) dbacc += __ldg(dy + m);
     }
   }
+#pragma unroll
+  for (int j = 0; j < D1_MAXG; ++j) red[warp][lane + 32 * j] = dwacc[j];
+  if (lane == 0) red[warp][D1_MAXG * 32] = dbacc;
   __syncthreads();
-  if (threadIdx.x < 32) dbacc = warp_sum(dbacc);
-  for (int k = threadIdx.x; k < K; k += 256) {
+  for (int k = threadIdx.x; k <= K; k += 256) {
+    const int col = k < K ? k : D1_MAXG * 32;
     float s0 = 0.f;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) s0 += colacc[j * (K + 1) + k];
+    for (int wv = 0; wv < 8; ++wv) s0 += red[wv][col];
     part[(int64_t)blockIdx.x * (K + 1) + k] = s0;
   }
-  if (threadIdx.x == 0) part[(int64_t)blockIdx.x * (K + 1) + K] = dbacc;
 }
 
 static inline bool vec_ok(const void* p, int64_t ld) { return aligned16(p) && ld % 4 == 0; }
@@ -562,13 +570,12 @@ HRB_API int hrb_dense1_bwd(const float* x, int64_t ldx, const float* w, const fl
   size_t need = 0;
   hrb_dense1_bwd_workspace(M, K, &need);
   if (workspace_bytes < need) return fail(HRB_WORKSPACE, "hrb_dense1_bwd: workspace %zu < required %zu bytes", workspace_bytes, need);
-  const size_t smem = (size_t)8 * (K + 1) * sizeof(float);
-  if (smem > 48 * 1024) return fail(HRB_UNSUPPORTED, "hrb_dense1_bwd: K=%d too wide", K);
+  if (K > D1_MAXG * 32) return fail(HRB_UNSUPPORTED, "hrb_dense1_bwd: K=%d > %d", K, D1_MAXG * 32);
   cudaStream_t st = (cudaStream_t)stream;
-  int grid = sm_count() * 8;  // 32-row slabs; enough CTAs to keep the loads of many slabs in flight
+  int grid = sm_count() * 4;
   if ((int64_t)grid * 32 > M) grid = (int)((M + 31) / 32);
   float* part = (float*)workspace;
-  dense1_bwd_kernel<<<grid, 256, smem, st>>>(x, ldx, w, dy, M, K, act_prev, dz_prev, lddz, dz_prev_t, lddzt, part);
+  dense1_bwd_kernel<<<grid, 256, 0, st>>>(x, ldx, w, dy, M, K, act_prev, dz_prev, lddz, dz_prev_t, lddzt, part);
   HRB_LAUNCH_CHECK();
   split_reduce_kernel<<<(K + 255) / 256, 256, 0, st>>>(part, 1, K, K + 1, grid, dw, K);
   HRB_LAUNCH_CHECK();

@@ -219,6 +219,15 @@ int hrb_dice_bwd(const float* x, const float* dy, int64_t rows, int32_t units, c
                  const float* mean, const float* var, float eps, int32_t training, float* dx, float* dalpha,
                  float* scratch /* 2*units floats, training only */, void* stream);
 
+/* Keras BatchNormalization (layers/core.py:71-72; last axis, biased batch variance in training) and Dropout
+ * (core.py:73; the keep mask is a pure function of (seed, element index): the backward is the same call on dy). */
+int hrb_batchnorm_fwd(const float* x, int64_t rows, int32_t units, const float* gamma, const float* beta, float* mean,
+                      float* var, float eps, int32_t training, float* y, void* stream);
+int hrb_batchnorm_bwd(const float* x, const float* dy, int64_t rows, int32_t units, const float* gamma, const float* mean,
+                      const float* var, float eps, int32_t training, float* dx, float* dgamma, float* dbeta,
+                      float* scratch /* 2*units floats */, void* stream);
+int hrb_dropout(const float* x, int64_t n, float rate, uint32_t seed, float* y, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * a10  LocalActivationUnit.call + SqueezeMask + tf.matmul(att, keys)
  *      (layers/sequence.py:92-102, layers/tools.py:104-113, models/ranking/sequential/DIN.py:87-93)
@@ -235,6 +244,18 @@ int hrb_lau_fwd(const float* table, int64_t vocab, int32_t dim, const int32_t* q
                 const int32_t* key_ids, int64_t batch, int32_t seq_len, const float* params,
                 const int32_t* layer_out_host, int32_t n_layers, int32_t act, float* score, float* pooled,
                 void* stream);
+
+/* a10, layer face (training path; the MLP between them is hrb_dense_* / hrb_dice_*):
+ *   att_input  out[b,t,:] = [q, k, q-k, q*k]  (sequence.py:96-97) and its backward (dq, dk)
+ *   mask_scores  out = mask ? s : 0           (sequence.py:100-101; its own backward)
+ *   att_pool   out[b,:] = sum_t s[b,t]*k[b,t,:]  (DIN.py:93) and its backward (ds, dk) */
+int hrb_att_input_fwd(const float* q, const float* k, int64_t batch, int32_t T, int32_t D, float* out, void* stream);
+int hrb_att_input_bwd(const float* q, const float* k, const float* g, int64_t batch, int32_t T, int32_t D, float* dq,
+                      float* dk, void* stream);
+int hrb_mask_scores(const float* s, const uint8_t* mask, int64_t n, float* out, void* stream);
+int hrb_att_pool_fwd(const float* s, const float* k, int64_t batch, int32_t T, int32_t D, float* out, void* stream);
+int hrb_att_pool_bwd(const float* s, const float* k, const float* dout, int64_t batch, int32_t T, int32_t D, float* ds,
+                     float* dk, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * DeepFM head + loss   (models/ranking/context_aware/DeepFM.py:86-88 + Keras binary_crossentropy)

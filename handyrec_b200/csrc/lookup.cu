@@ -14,6 +14,8 @@
 // the DNN input (B, sum D) and the FM input (B, F, D) are the same bytes (layers/utils.py:40-96).
 #include <cub/device/device_radix_sort.cuh>
 #include <new>
+#include <stdlib.h>
+#include <string.h>
 #include <vector>
 
 #include "common.cuh"
@@ -406,6 +408,106 @@ __global__ void __launch_bounds__(256) lookup_rows_kernel(const FieldDev* __rest
       if (valid && q == 0) fm_out[b] = p2 + 0.5f * p3 + w0;
       if (valid && fm_sum != nullptr) reinterpret_cast<float4*>(fm_sum + b * (int64_t)(G * 4))[q] = S;
     }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// a7 + a9, plain-lookup groups (Criteo shape), v2: the gather never touches registers.
+//   One CTA owns tiles of 32 samples.  Every row is copied global -> shared with 16-byte cp.async (LDGSTS),
+//   all F*D/4 copies of a thread in flight at once; the FM sums are taken from shared memory; each sample's
+//   F*D-float output row leaves as ONE bulk TMA store (cp.async.bulk shared -> global, full lines).
+//   Shared tile pitch = F*D*4 + pad so that two neighbouring samples sit 64 B apart mod 128 (conflict-free LDS.128).
+//   ~54 KB per CTA at F=26, D=16 -> 4 CTAs/SM, 200+ KB of gathers in flight per SM with ~40 registers/thread.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_addr_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+template <int G, bool FM>
+__global__ void __launch_bounds__(32 * G) lookup_tile_kernel(const FieldDev* __restrict__ fields_g, int32_t n_fields,
+                                                            const int32_t* __restrict__ ids, int64_t ids_ld, int64_t batch,
+                                                            float* __restrict__ out, int64_t out_ld, int32_t pitch /* floats */,
+                                                            const float* __restrict__ fm_w, const float* __restrict__ fm_w0,
+                                                            float* __restrict__ fm_out, float* __restrict__ fm_sum,
+                                                            int32_t* __restrict__ oob) {
+  constexpr int TS = 32;            // samples per tile
+  constexpr int NT = 32 * G;        // threads: G lanes per sample
+  constexpr int D = 4 * G;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float* tile = reinterpret_cast<float*>(smem_raw);                                   // [TS][pitch]
+  FieldDev* fields = reinterpret_cast<FieldDev*>(smem_raw + (size_t)TS * pitch * 4);  // descriptors
+  for (int i = threadIdx.x; i < n_fields * (int)(sizeof(FieldDev) / 4); i += NT)
+    reinterpret_cast<uint32_t*>(fields)[i] = reinterpret_cast<const uint32_t*>(fields_g)[i];
+  __syncthreads();
+  const int q = threadIdx.x % G, s = threadIdx.x / G;
+  float4 w4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  float w0 = 0.f;
+  if (FM) {
+    w4 = __ldg(reinterpret_cast<const float4*>(fm_w) + q);
+    w0 = __ldg(fm_w0);
+  }
+  const int out_col0 = fields[0].out_col;
+  const uint32_t row_bytes = (uint32_t)(n_fields * D * 4);
+  const int64_t n_tiles = (batch + TS - 1) / TS;
+  for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+    const int64_t b = t * TS + s;
+    const bool valid = b < batch;
+    const int32_t* ids_row = ids + (valid ? b : 0) * ids_ld;
+    float* my_row = tile + (size_t)s * pitch;
+    // gather: ids first (independent loads), then one 16-byte async copy per (field, chunk)
+    constexpr int FU = 13;
+    for (int f0 = 0; f0 < n_fields; f0 += FU) {
+      int32_t id[FU];
+#pragma unroll
+      for (int u = 0; u < FU; ++u) id[u] = (valid && f0 + u < n_fields) ? __ldg(ids_row + fields[f0 + u].ids_col) : 0;
+#pragma unroll
+      for (int u = 0; u < FU; ++u) {
+        if (f0 + u < n_fields) {
+          const FieldDev& f = fields[f0 + u];
+          float* dst = my_row + (f0 + u) * D + q * 4;
+          if (valid && id[u] >= 0 && (int64_t)id[u] < f.rows) {
+            const float* src = f.table + (int64_t)id[u] * D + q * 4;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr_u32(dst)), "l"(src) : "memory");
+          } else {
+            *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (valid && oob != nullptr) {
+              oob[0] = 1;
+              oob[1] = (int32_t)b;
+            }
+          }
+        }
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // rows must be visible to the bulk-store engine
+    __syncthreads();
+    // one bulk store per sample row (1664 B at F=26, D=16): shared -> global, full lines
+    if (q == 0 && valid)
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(out + b * out_ld + out_col0),
+                   "r"(smem_addr_u32(my_row)), "r"(row_bytes)
+                   : "memory");
+    if (q == 0) asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    if (FM) {
+      float4 S = make_float4(0.f, 0.f, 0.f, 0.f), Q = make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4* r4 = reinterpret_cast<const float4*>(my_row) + q;
+#pragma unroll 2
+      for (int f = 0; f < n_fields; ++f) {
+        const float4 v = r4[f * G];
+        S.x += v.x; S.y += v.y; S.z += v.z; S.w += v.w;
+        Q.x = fmaf(v.x, v.x, Q.x); Q.y = fmaf(v.y, v.y, Q.y); Q.z = fmaf(v.z, v.z, Q.z); Q.w = fmaf(v.w, v.w, Q.w);
+      }
+      float p2 = S.x * w4.x + S.y * w4.y + S.z * w4.z + S.w * w4.w;
+      float p3 = (S.x * S.x - Q.x) + (S.y * S.y - Q.y) + (S.z * S.z - Q.z) + (S.w * S.w - Q.w);
+#pragma unroll
+      for (int o = G / 2; o > 0; o >>= 1) {
+        p2 += __shfl_xor_sync(0xffffffffu, p2, o, G);
+        p3 += __shfl_xor_sync(0xffffffffu, p3, o, G);
+      }
+      if (valid && q == 0) fm_out[b] = p2 + 0.5f * p3 + w0;
+      if (valid && fm_sum != nullptr) reinterpret_cast<float4*>(fm_sum + b * (int64_t)D)[q] = S;
+    }
+    // the tile is rewritten next iteration: the bulk stores must have finished READING it
+    if (q == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    __syncthreads();
   }
 }
 
@@ -955,6 +1057,43 @@ static int launch_rows(const hrb_plan* plan, const int32_t* ids, int64_t ids_ld,
                        int64_t out_ld, float* inv_count, const float* fm_w, const float* fm_w0, float* fm_out,
                        float* fm_sum, int32_t* oob, cudaStream_t st) {
   const int G = plan->max_dim / 4;
+  // v2 tile kernel for plain-lookup groups laid out contiguously (the Criteo shape)
+  static int use_tile = -1;
+  if (use_tile < 0) {
+    const char* e = getenv("HRB_LOOKUP_KERNEL");
+    use_tile = (e != nullptr && strcmp(e, "rows") == 0) ? 0 : 1;
+  }
+  if (use_tile && inv_count == nullptr && plan->all_len1 && plan->contiguous_out && (G == 2 || G == 4 || G == 8 || G == 16) && aligned16(out) &&
+      (out_ld % 4 == 0) && (plan->fdev_host[0].out_col % 4 == 0)) {
+    int pitch = plan->n_fields * plan->max_dim;       // floats
+    while ((pitch / 4) % 8 != 4) pitch += 4;            // neighbouring samples 64 B apart mod 128
+    const size_t smem = (size_t)32 * pitch * 4 + sizeof(FieldDev) * (size_t)plan->n_fields;
+    if (smem <= 100 * 1024) {
+      const int per_sm = (int)((220 * 1024) / (smem + 1024));
+      int64_t tiles = (batch + 31) / 32;
+      int64_t grid = (int64_t)sm_count() * (per_sm < 1 ? 1 : (per_sm > 8 ? 8 : per_sm));
+      if (grid > tiles) grid = tiles;
+#define HRB_TILE(GG)                                                                                                          \
+  {                                                                                                                           \
+    static bool attr = false;                                                                                                 \
+    if (!attr) {                                                                                                              \
+      HRB_CUDA(cudaFuncSetAttribute(lookup_tile_kernel<GG, FM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));    \
+      attr = true;                                                                                                            \
+    }                                                                                                                         \
+    lookup_tile_kernel<GG, FM><<<(unsigned)grid, 32 * GG, smem, st>>>(plan->d_fields, plan->n_fields, ids, ids_ld, batch, out, \
+                                                                      out_ld, pitch, fm_w, fm_w0, fm_out, fm_sum, oob);       \
+  }
+      switch (G) {
+        case 2: HRB_TILE(2) break;
+        case 4: HRB_TILE(4) break;
+        case 8: HRB_TILE(8) break;
+        default: HRB_TILE(16) break;
+      }
+#undef HRB_TILE
+      HRB_LAUNCH_CHECK();
+      return HRB_OK;
+    }
+  }
   const int spb = 256 / G;
   // enough CTAs for every SM to hold its full complement, persistent-style grid-stride over samples
   int64_t blocks = (batch + spb - 1) / spb;
@@ -990,6 +1129,11 @@ HRB_API int hrb_lookup_fwd(const hrb_plan* plan, const int32_t* ids, int64_t ids
   int rc = check_lookup_args("hrb_lookup_fwd", plan, ids, ids_ld, batch, out, out_ld);
   if (rc != HRB_OK) return rc;
   if (batch == 0) return HRB_OK;
+  if (inv_count == nullptr && plan->all_len1 && plan->uniform_dim && plan->contiguous_out) {
+    const int G = plan->max_dim / 4;
+    if (G == 2 || G == 4 || G == 8 || G == 16)  // plain-lookup group: the cp.async / bulk-store tile kernel without the FM epilogue
+      return launch_rows<false>(plan, ids, ids_ld, batch, out, out_ld, nullptr, nullptr, nullptr, nullptr, nullptr, oob, (cudaStream_t)stream);
+  }
   const unsigned grid = grid_for(batch * plan->out_chunks, 256, 8);
   lookup_items_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(plan->d_fields, plan->d_chunk_field,
                                                                     plan->d_chunk_q, plan->out_chunks, plan->n_fields,

@@ -153,13 +153,13 @@ class LookupPlan:
         self._ws = None
 
     def __del__(self):
-        h = getattr(self, "_h", None)
-        if h is not None and h.value:
-            try:
+        try:  # module globals may already be gone at interpreter shutdown
+            h = getattr(self, "_h", None)
+            if h is not None and h.value:
                 _lib.lib().hrb_plan_destroy(h)
-            except Exception:
-                pass
-            self._h = ctypes.c_void_p(0)
+                self._h = None
+        except Exception:
+            pass
 
     def _ids_ld(self, ids: torch.Tensor) -> int:
         _chk(ids, torch.int32, "ids", contiguous=False)

@@ -189,6 +189,37 @@ __global__ void __launch_bounds__(256) split_reduce_kernel(const float* __restri
   }
 }
 
+// many partials per output (split counts in the hundreds): one warp per output element, lanes stride over the
+// partials (independent loads in flight), fixed-shape tree at the end -> still deterministic
+__global__ void __launch_bounds__(256) split_reduce_wide_kernel(const float* __restrict__ part, int64_t rows, int32_t cols,
+                                                               int64_t ld_part, int32_t splits, float* __restrict__ out,
+                                                               int64_t ld_out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int64_t total = rows * cols;
+  for (int64_t i = warp0; i < total; i += nwarps) {
+    const int64_t r = i / cols;
+    const int c = (int)(i - r * cols);
+    float s = 0.f;
+    for (int z = lane; z < splits; z += 32) s += __ldg(part + ((int64_t)z * rows + r) * ld_part + c);
+    s = warp_sum(s);
+    if (lane == 0) out[r * ld_out + c] = s;
+  }
+}
+
+static inline void launch_split_reduce(const float* part, int64_t rows, int32_t cols, int64_t ld_part, int32_t splits, float* out,
+                                       int64_t ld_out, cudaStream_t st) {
+  const int64_t total = rows * cols;
+  if (splits > 16 && total * 32 <= (int64_t)sm_count() * 2048 * 4) {
+    const int64_t blocks = min((int64_t)sm_count() * 8, (total * 32 + 255) / 256);
+    split_reduce_wide_kernel<<<(unsigned)blocks, 256, 0, st>>>(part, rows, cols, ld_part, splits, out, ld_out);
+  } else {
+    const int64_t blocks = min((int64_t)sm_count() * 4, (total + 255) / 256);
+    split_reduce_kernel<<<(unsigned)(blocks < 1 ? 1 : blocks), 256, 0, st>>>(part, rows, cols, ld_part, splits, out, ld_out);
+  }
+}
+
 // column sums of dz[M,N] (bias gradient), two fixed-order passes: per-CTA partials then a final sum
 __global__ void __launch_bounds__(256) colsum_partial_kernel(const float* __restrict__ dz, int64_t lddz, int64_t M,
                                                             int32_t N, int64_t rows_per_block,
@@ -443,8 +474,7 @@ HRB_API int hrb_dense_bwd_w(const float* x, int64_t ldx, const float* dz, int64_
     GemmArgs g{x, dz, part, ldx, lddz, ldp, K, N, M, nullptr, nullptr, 0, 0, kslice};
     int rc = launch_sgemm<true, false, EPI_PLAIN>(g, eff_splits, st);
     if (rc != HRB_OK) return rc;
-    split_reduce_kernel<<<(unsigned)min((int64_t)sm_count() * 4, ((int64_t)K * N + 255) / 256), 256, 0, st>>>(
-        part, K, N, ldp, eff_splits, dw, lddw);
+    launch_split_reduce(part, K, N, ldp, eff_splits, dw, lddw, st);
     HRB_LAUNCH_CHECK();
   }
   if (dbias != nullptr) {
@@ -454,7 +484,7 @@ HRB_API int hrb_dense_bwd_w(const float* x, int64_t ldx, const float* dz, int64_
     dim3 grid((N + 31) / 32, yb);
     colsum_partial_kernel<<<grid, 256, 0, st>>>(dz, lddz, M, N, rpb, colpart);
     HRB_LAUNCH_CHECK();
-    split_reduce_kernel<<<(N + 255) / 256, 256, 0, st>>>(colpart, 1, N, N, yb, dbias, N);
+    launch_split_reduce(colpart, 1, N, N, yb, dbias, N, st);
     HRB_LAUNCH_CHECK();
   }
   return HRB_OK;
@@ -527,7 +557,7 @@ HRB_API int hrb_dense_bwd_w_t(const float* xt, int64_t ldxt, const float* dzt, i
   float* colpart = part + (size_t)splits * K * ldp;
   int rc = hrb_tc_gemm_splitk(xt, ldxt, dzt, lddzt, K, N, (int32_t)M, splits, part, ldp, st);
   if (rc != HRB_OK) return rc;
-  split_reduce_kernel<<<(unsigned)min((int64_t)sm_count() * 4, ((int64_t)K * N + 255) / 256), 256, 0, st>>>(part, K, N, ldp, splits, dw, lddw);
+  launch_split_reduce(part, K, N, ldp, splits, dw, lddw, st);
   HRB_LAUNCH_CHECK();
   if (dbias != nullptr) {
     int yb = (int)min((int64_t)256, (M + 255) / 256);
@@ -535,7 +565,7 @@ HRB_API int hrb_dense_bwd_w_t(const float* xt, int64_t ldxt, const float* dzt, i
     dim3 grid((N + 31) / 32, yb);
     colsum_partial_kernel<<<grid, 256, 0, st>>>(dz, lddz, M, N, rpb, colpart);
     HRB_LAUNCH_CHECK();
-    split_reduce_kernel<<<(N + 255) / 256, 256, 0, st>>>(colpart, 1, N, N, yb, dbias, N);
+    launch_split_reduce(colpart, 1, N, N, yb, dbias, N, st);
     HRB_LAUNCH_CHECK();
   }
   return HRB_OK;
@@ -577,10 +607,10 @@ HRB_API int hrb_dense1_bwd(const float* x, int64_t ldx, const float* w, const fl
   float* part = (float*)workspace;
   dense1_bwd_kernel<<<grid, 256, 0, st>>>(x, ldx, w, dy, M, K, act_prev, dz_prev, lddz, dz_prev_t, lddzt, part);
   HRB_LAUNCH_CHECK();
-  split_reduce_kernel<<<(K + 255) / 256, 256, 0, st>>>(part, 1, K, K + 1, grid, dw, K);
+  launch_split_reduce(part, 1, K, K + 1, grid, dw, K, st);
   HRB_LAUNCH_CHECK();
   if (dbias != nullptr) {
-    split_reduce_kernel<<<1, 256, 0, st>>>(part + K, 1, 1, K + 1, grid, dbias, 1);
+    launch_split_reduce(part + K, 1, 1, K + 1, grid, dbias, 1, st);
     HRB_LAUNCH_CHECK();
   }
   return HRB_OK;

@@ -273,74 +273,58 @@ __global__ void __launch_bounds__(256) dense1_fwd_kernel(const float* __restrict
   }
 }
 
-// dz_prev[m,k] = dy[m] * w[k] * act'(x[m,k]) (+ transposed copy), dw[k] = sum_m x[m,k]*dy[m], db = sum_m dy[m]
-// 8 warps x 4 rows = one 32-row slab per pass; lane l owns columns l, l+32, ... (coalesced 128-byte accesses),
-// weight-gradient partials stay in registers across slabs; the transposed copy goes through a padded smem tile so
-// that its stores run along m.  Per-CTA partials land in `part` ([grid][K+1]) for a fixed-order reduce.
-constexpr int D1_MAXG = 16;  // K <= 512
-__global__ void __launch_bounds__(256) dense1_bwd_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ w,
-                                                        const float* __restrict__ dy, int64_t M, int32_t K, int32_t act,
-                                                        float* __restrict__ dzp, int64_t lddz, float* __restrict__ dzt, int64_t lddzt,
-                                                        float* __restrict__ part) {
-  __shared__ float tile[32][129];
-  __shared__ float red[8][D1_MAXG * 32 + 1];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int groups = (K + 31) / 32;
-  float wk[D1_MAXG], dwacc[D1_MAXG];
-#pragma unroll
-  for (int j = 0; j < D1_MAXG; ++j) {
-    const int k = lane + 32 * j;
-    wk[j] = (j < groups && k < K) ? __ldg(w + k) : 0.f;
-    dwacc[j] = 0.f;
+// Backward of the 1-unit layer as three streaming kernels:
+//   (1) dz_prev[m,k] = dy[m] * w[k] * act'(x[m,k])            element-wise, float4
+//   (2) dz_prev^T via hrb_transpose_kernel                      (only when the tensor-core bwd_w needs it)
+//   (3) dw[k] = sum_m x[m,k]*dy[m], db = sum_m dy[m]            per-slab partials + fixed-order reduce
+__global__ void __launch_bounds__(256) dense1_bwd_dz_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ w,
+                                                           const float* __restrict__ dy, int64_t M, int32_t K4 /* K/4 */, int32_t act,
+                                                           float* __restrict__ dzp, int64_t lddz) {
+  const int64_t total = M * K4;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t m = i / K4;
+    const int c = (int)(i - m * K4);
+    const float4 xv = __ldg(reinterpret_cast<const float4*>(x + m * ldx) + c);
+    const float4 wv = __ldg(reinterpret_cast<const float4*>(w) + c);
+    const float g = __ldg(dy + m);
+    float4 o;
+    o.x = g * wv.x * act_grad_from_out(act, xv.x);
+    o.y = g * wv.y * act_grad_from_out(act, xv.y);
+    o.z = g * wv.z * act_grad_from_out(act, xv.z);
+    o.w = g * wv.w * act_grad_from_out(act, xv.w);
+    reinterpret_cast<float4*>(dzp + m * lddz)[c] = o;
   }
-  float dbacc = 0.f;
-  for (int64_t row0 = (int64_t)blockIdx.x * 32; row0 < M; row0 += (int64_t)gridDim.x * 32) {
-#pragma unroll
-    for (int pass = 0; pass < D1_MAXG / 4; ++pass) {  // 128 columns per pass through the tile (unrolled: register arrays)
-      const int g0 = pass * 4;
-      if (g0 >= groups) break;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int r = warp * 4 + i;
-        const int64_t m = row0 + r;
-        const float g = m < M ? __ldg(dy + m) : 0.f;
-        if (g0 == 0 && lane == 0) dbacc += g;
-#pragma unroll
-        for (int jj = 0; jj < 4; ++jj) {
-          const int j = pass * 4 + jj;
-          const int k = lane + 32 * j;
-          float t = 0.f;
-          if (j < groups && k < K && m < M) {
-            const float xv = __ldg(x + m * ldx + k);
-            dwacc[j] = fmaf(xv, g, dwacc[j]);
-            t = g * wk[j] * act_grad_from_out(act, xv);
-            dzp[m * lddz + k] = t;
-          }
-          tile[r][lane + 32 * jj] = t;
-        }
-      }
-      if (dzt != nullptr) {
-        __syncthreads();
-#pragma unroll
-        for (int c = warp * 16; c < warp * 16 + 16; ++c) {  // 128 tile columns, 16 per warp; lanes run along m
-          const int k = g0 * 32 + c;
-          const int64_t m = row0 + lane;
-          if (k < K && m < M) dzt[(int64_t)k * lddzt + m] = tile[lane][c];
-        }
-        __syncthreads();
-      }
-    }
+}
+
+// part[blockIdx.y][k] = sum over the row slab of x[m,k]*dy[m]; part[blockIdx.y][K] = sum dy  (32 columns x 8 row lanes)
+__global__ void __launch_bounds__(256) dense1_bwd_dw_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ dy,
+                                                           int64_t M, int32_t K, int64_t rows_per_block, float* __restrict__ part) {
+  const int k = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int ry = threadIdx.x >> 5;
+  __shared__ float red[8][33], redb[8];
+  const int64_t r0 = (int64_t)blockIdx.y * rows_per_block, r1 = min(M, r0 + rows_per_block);
+  float s = 0.f, sb = 0.f;
+  for (int64_t m = r0 + ry; m < r1; m += 8) {
+    const float g = __ldg(dy + m);
+    if (k < K) s = fmaf(__ldg(x + m * ldx + k), g, s);
+    if (blockIdx.x == 0 && (threadIdx.x & 31) == 0) sb += g;
   }
-#pragma unroll
-  for (int j = 0; j < D1_MAXG; ++j) red[warp][lane + 32 * j] = dwacc[j];
-  if (lane == 0) red[warp][D1_MAXG * 32] = dbacc;
+  red[ry][threadIdx.x & 31] = s;
+  if ((threadIdx.x & 31) == 0) redb[ry] = sb;
   __syncthreads();
-  for (int k = threadIdx.x; k <= K; k += 256) {
-    const int col = k < K ? k : D1_MAXG * 32;
-    float s0 = 0.f;
+  if (ry == 0) {
+    if (k < K) {
+      float t = 0.f;
 #pragma unroll
-    for (int wv = 0; wv < 8; ++wv) s0 += red[wv][col];
-    part[(int64_t)blockIdx.x * (K + 1) + k] = s0;
+      for (int j = 0; j < 8; ++j) t += red[j][threadIdx.x & 31];
+      part[(int64_t)blockIdx.y * (K + 1) + k] = t;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+      float t = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) t += redb[j];
+      part[(int64_t)blockIdx.y * (K + 1) + K] = t;
+    }
   }
 }
 
@@ -587,7 +571,7 @@ HRB_API int hrb_dense1_fwd(const float* x, int64_t ldx, const float* w, const fl
 
 HRB_API int hrb_dense1_bwd_workspace(int64_t M, int32_t K, size_t* bytes) {
   HRB_REQUIRE(bytes && M >= 0 && K > 0, "hrb_dense1_bwd_workspace: bad argument");
-  *bytes = (size_t)sm_count() * 8 * (K + 1) * sizeof(float) + 256;
+  *bytes = (size_t)512 * (K + 1) * sizeof(float) + 256;
   return HRB_OK;
 }
 
@@ -597,20 +581,33 @@ HRB_API int hrb_dense1_bwd(const float* x, int64_t ldx, const float* w, const fl
                            size_t workspace_bytes, void* stream) {
   HRB_REQUIRE(x && w && dy && dz_prev && dw && workspace && M > 0 && K > 0 && ldx >= K && lddz >= K, "hrb_dense1_bwd: bad argument");
   HRB_REQUIRE(dz_prev_t == nullptr || lddzt >= M, "hrb_dense1_bwd: lddzt < M");
+  if (K % 4 != 0 || ldx % 4 != 0 || lddz % 4 != 0 || !aligned16(x) || !aligned16(w) || !aligned16(dz_prev))
+    return fail(HRB_UNSUPPORTED, "hrb_dense1_bwd: needs K, ldx, lddz multiples of 4 and 16-byte aligned buffers");
   size_t need = 0;
   hrb_dense1_bwd_workspace(M, K, &need);
   if (workspace_bytes < need) return fail(HRB_WORKSPACE, "hrb_dense1_bwd: workspace %zu < required %zu bytes", workspace_bytes, need);
-  if (K > D1_MAXG * 32) return fail(HRB_UNSUPPORTED, "hrb_dense1_bwd: K=%d > %d", K, D1_MAXG * 32);
   cudaStream_t st = (cudaStream_t)stream;
-  int grid = sm_count() * 4;
-  if ((int64_t)grid * 32 > M) grid = (int)((M + 31) / 32);
-  float* part = (float*)workspace;
-  dense1_bwd_kernel<<<grid, 256, 0, st>>>(x, ldx, w, dy, M, K, act_prev, dz_prev, lddz, dz_prev_t, lddzt, part);
+  const int64_t total = M * (K / 4);
+  const int64_t blocks = min((int64_t)sm_count() * 8, (total + 255) / 256);
+  dense1_bwd_dz_kernel<<<(unsigned)blocks, 256, 0, st>>>(x, ldx, w, dy, M, K / 4, act_prev, dz_prev, lddz);
   HRB_LAUNCH_CHECK();
-  launch_split_reduce(part, 1, K, K + 1, grid, dw, K, st);
+  if (dz_prev_t != nullptr) {
+    dim3 tg((K + 31) / 32, (unsigned)((M + 31) / 32));
+    if (tg.y > 65535) return fail(HRB_UNSUPPORTED, "hrb_dense1_bwd: M > 2M rows");
+    hrb_transpose_kernel<<<tg, 256, 0, st>>>(dz_prev, M, K, lddz, dz_prev_t, lddzt);
+    HRB_LAUNCH_CHECK();
+  }
+  int yb = (int)min((int64_t)512, (M + 127) / 128);
+  if (yb < 1) yb = 1;
+  const int64_t rpb = (M + yb - 1) / yb;
+  float* part = (float*)workspace;
+  dim3 grid((K + 31) / 32, yb);
+  dense1_bwd_dw_kernel<<<grid, 256, 0, st>>>(x, ldx, dy, M, K, rpb, part);
+  HRB_LAUNCH_CHECK();
+  launch_split_reduce(part, 1, K, K + 1, yb, dw, K, st);
   HRB_LAUNCH_CHECK();
   if (dbias != nullptr) {
-    launch_split_reduce(part + K, 1, 1, K + 1, grid, dbias, 1, st);
+    launch_split_reduce(part + K, 1, 1, K + 1, yb, dbias, 1, st);
     HRB_LAUNCH_CHECK();
   }
   return HRB_OK;

@@ -68,6 +68,9 @@ struct hrb_plan {
   int32_t* d_chunk_field = nullptr;  // out chunk -> field
   int32_t* d_chunk_q = nullptr;      // out chunk -> 4-column group inside the field
   int32_t* d_pos_field = nullptr;    // position column -> field
+  uint32_t* d_hot_keys = nullptr;    // keys of every row of the tiny ("hot") tables (see bwd_hot_kernel)
+  int32_t n_hot_keys = 0;
+  std::vector<uint32_t> hot_lo, hot_len;
 };
 
 namespace hrb {
@@ -702,6 +705,102 @@ __device__ __forceinline__ void apply_row(const ApplyCtx& c, uint32_t key, int q
   *wp = w;
 }
 
+// Rows of tiny tables (vocab <= HOT_MAX_ROWS) collect thousands of duplicates per step (65536/V each at the Criteo
+// shape).  They are taken out of the chunk/merge path: one CTA per such row finds the row's run in the sorted keys by
+// binary search and reduces it with all its lanes (fixed assignment + fixed-order tree -> deterministic).
+constexpr int HOT_MAX_ROWS = 128;   // 65536/128 = 512 duplicates per row at the bench batch: chains of >= 32 chunks
+constexpr int HOT_SLICES = 8;      // CTAs per hot row (stage 1); stage 2 adds the slices in order
+constexpr int HOT_MAX_RANGES = 32;
+struct HotInfo {
+  int32_t n_ranges;
+  uint32_t lo[HOT_MAX_RANGES];
+  uint32_t len[HOT_MAX_RANGES];
+  const uint32_t* keys;  // key of hot row i (nullptr: key = i)
+  int32_t n_keys;
+};
+__device__ __forceinline__ bool is_hot(const HotInfo& h, uint32_t key) {
+  bool hot = false;
+  for (int r = 0; r < h.n_ranges; ++r) hot |= (key - h.lo[r]) < h.len[r];
+  return hot;
+}
+
+// stage 1: CTA (row, slice) reduces its slice of the row's run -> hot_partial[(row*HOT_SLICES + slice)][G*4]
+template <typename GradSrc>
+__global__ void __launch_bounds__(256) bwd_hot_slice_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals,
+                                                           int64_t n, int G, GradSrc src, HotInfo hot, float* __restrict__ hot_partial) {
+  __shared__ int64_t s_lo, s_hi;
+  __shared__ float4 red[256];
+  const int row = blockIdx.x / HOT_SLICES, slice = blockIdx.x % HOT_SLICES;
+  const uint32_t key = hot.keys != nullptr ? hot.keys[row] : (uint32_t)row;
+  if (threadIdx.x == 0) {
+    int64_t lo = 0, hi = n;
+    while (lo < hi) {  // lower_bound(key)
+      const int64_t mid = (lo + hi) >> 1;
+      if (__ldg(keys + mid) < key) lo = mid + 1; else hi = mid;
+    }
+    s_lo = lo;
+    hi = n;
+    while (lo < hi) {  // upper_bound(key)
+      const int64_t mid = (lo + hi) >> 1;
+      if (__ldg(keys + mid) <= key) lo = mid + 1; else hi = mid;
+    }
+    s_hi = lo;
+  }
+  __syncthreads();
+  const int64_t len = s_hi - s_lo;
+  const int64_t lo = s_lo + len * slice / HOT_SLICES, hi = s_lo + len * (slice + 1) / HOT_SLICES;
+  const int groups = blockDim.x / G;
+  const int q = threadIdx.x % G, g = threadIdx.x / G;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (g < groups) {
+    constexpr int U = 4;
+    for (int64_t i0 = lo + g; i0 < hi; i0 += (int64_t)groups * U) {
+      float4 v[U];
+      float sc[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int64_t i = i0 + (int64_t)u * groups;
+        v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        sc[u] = 0.f;
+        if (i < hi) v[u] = src.load(__ldg(vals + i), q, sc[u]);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        acc.x = fmaf(v[u].x, sc[u], acc.x); acc.y = fmaf(v[u].y, sc[u], acc.y);
+        acc.z = fmaf(v[u].z, sc[u], acc.z); acc.w = fmaf(v[u].w, sc[u], acc.w);
+      }
+    }
+  }
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int stride = 128; stride >= G; stride >>= 1) {  // fixed-order tree over the groups (same q: G apart)
+    if (threadIdx.x < stride && threadIdx.x + stride < groups * G) {
+      const float4 o = red[threadIdx.x + stride];
+      float4 m = red[threadIdx.x];
+      m.x += o.x; m.y += o.y; m.z += o.z; m.w += o.w;
+      red[threadIdx.x] = m;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x < G) reinterpret_cast<float4*>(hot_partial + (size_t)blockIdx.x * (G * 4))[threadIdx.x] = red[threadIdx.x];
+  if (threadIdx.x == 0 && slice == 0) hot_partial[(size_t)gridDim.x * (G * 4) + row] = (float)(len > 0);  // touched flag
+}
+// stage 2: one group per hot row adds its slices in order and updates the row
+template <int MODE>
+__global__ void __launch_bounds__(256) bwd_hot_apply_kernel(int n_rows, int G, ApplyCtx ctx, HotInfo hot, const float* __restrict__ hot_partial) {
+  const int gpb = blockDim.x / G;
+  const int row = blockIdx.x * gpb + threadIdx.x / G, q = threadIdx.x % G;
+  if (threadIdx.x / G >= gpb || row >= n_rows) return;
+  if (hot_partial[(size_t)n_rows * HOT_SLICES * (G * 4) + row] == 0.f) return;  // row not touched by this batch
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int sl = 0; sl < HOT_SLICES; ++sl) {
+    const float4 v = reinterpret_cast<const float4*>(hot_partial + ((size_t)row * HOT_SLICES + sl) * (G * 4))[q];
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  }
+  apply_row<MODE>(ctx, hot.keys != nullptr ? hot.keys[row] : (uint32_t)row, q, acc);
+}
+
 // Step 3: chunk kernel.  G lanes own CH consecutive sorted positions.  Runs (equal keys) that lie
 // strictly inside the chunk are final and update their row at once; the (at most two) runs that
 // touch a chunk edge and continue across it go to the partial buffer (slot 0 = head, 1 = tail).
@@ -713,7 +812,7 @@ __global__ void __launch_bounds__(256) bwd_chunk_kernel(const uint32_t* __restri
                                                        const uint32_t* __restrict__ vals, int64_t n,
                                                        uint32_t sentinel, int G, GradSrc src, ApplyCtx ctx,
                                                        float* __restrict__ partial /* (2*chunks, G*4) */,
-                                                       uint32_t* __restrict__ pkey, uint32_t* __restrict__ pflag) {
+                                                       uint32_t* __restrict__ pkey, uint32_t* __restrict__ pflag, HotInfo hot) {
   const int groups_per_block = blockDim.x / G;
   const int q = threadIdx.x % G;
   const int g_in_block = threadIdx.x / G;
@@ -725,7 +824,10 @@ __global__ void __launch_bounds__(256) bwd_chunk_kernel(const uint32_t* __restri
     uint32_t k[CH];
     float4 g[CH];
 #pragma unroll
-    for (int j = 0; j < CH; ++j) k[j] = (i0 + j < n) ? __ldg(keys + i0 + j) : sentinel;
+    for (int j = 0; j < CH; ++j) {
+      k[j] = (i0 + j < n) ? __ldg(keys + i0 + j) : sentinel;
+      if (k[j] != sentinel && is_hot(hot, k[j])) k[j] = sentinel;  // rows of tiny tables belong to bwd_hot_kernel
+    }
 #pragma unroll
     for (int j = 0; j < CH; ++j) {
       g[j] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -735,8 +837,10 @@ __global__ void __launch_bounds__(256) bwd_chunk_kernel(const uint32_t* __restri
         g[j] = make_float4(v.x * s, v.y * s, v.z * s, v.w * s);
       }
     }
-    const uint32_t kprev = i0 > 0 ? __ldg(keys + i0 - 1) : sentinel;
-    const uint32_t knext = (i0 + CH < n) ? __ldg(keys + i0 + CH) : sentinel;
+    uint32_t kprev = i0 > 0 ? __ldg(keys + i0 - 1) : sentinel;
+    uint32_t knext = (i0 + CH < n) ? __ldg(keys + i0 + CH) : sentinel;
+    if (kprev != sentinel && is_hot(hot, kprev)) kprev = sentinel;
+    if (knext != sentinel && is_hot(hot, knext)) knext = sentinel;
     if (q == 0) {
       pflag[2 * chunk] = 0;
       pflag[2 * chunk + 1] = 0;
@@ -833,7 +937,7 @@ static inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a
 
 struct BwdWorkspace {
   uint32_t *keys_in, *keys_out, *vals_in, *vals_out, *pkey, *pflag;
-  float *scale, *partial;
+  float *scale, *partial, *hot_partial;
   void* cub_tmp;
   size_t cub_bytes;
   size_t total;
@@ -855,6 +959,7 @@ static int carve_bwd_ws(int64_t n, int64_t scale_elems, int max_dim, int key_bit
   w.partial = (float*)take((size_t)n_chunks * 2 * max_dim * 4);
   w.pkey = (uint32_t*)take((size_t)n_chunks * 2 * 4);
   w.pflag = (uint32_t*)take((size_t)n_chunks * 2 * 4);
+  w.hot_partial = (float*)take((size_t)HOT_MAX_RANGES * HOT_MAX_ROWS * (HOT_SLICES * max_dim + 1) * 4);
   size_t cub_bytes = 0;
   cudaError_t e = cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr,
                                                   (const uint32_t*)nullptr, (uint32_t*)nullptr, (int)n, 0, key_bits);
@@ -871,9 +976,26 @@ static int bits_for(uint64_t max_value) {
   return b;
 }
 
+static HotInfo hot_from_plan(const hrb_plan* plan) {
+  HotInfo h{};
+  h.n_ranges = (int32_t)plan->hot_lo.size();
+  for (int i = 0; i < h.n_ranges; ++i) {
+    h.lo[i] = plan->hot_lo[i];
+    h.len[i] = plan->hot_len[i];
+  }
+  h.keys = plan->d_hot_keys;
+  h.n_keys = plan->n_hot_keys;
+  return h;
+}
+
 template <typename GradSrc>
 static int run_sorted_update(int mode, const BwdWorkspace& w, int64_t n, uint32_t sentinel, int key_bits, int G,
-                             GradSrc src, ApplyCtx ctx, cudaStream_t st) {
+                             GradSrc src, ApplyCtx ctx, const HotInfo& hot_in, cudaStream_t st) {
+  HotInfo hot = hot_in;
+  if ((G & (G - 1)) != 0 || G > 128) {  // the hot-row tree reduction pairs lanes a power of two apart
+    hot.n_keys = 0;
+    hot.n_ranges = 0;
+  }
   size_t cub_bytes = w.cub_bytes;
   HRB_CUDA(cub::DeviceRadixSort::SortPairs(w.cub_tmp, cub_bytes, w.keys_in, w.keys_out, w.vals_in, w.vals_out,
                                            (int)n, 0, key_bits, st));
@@ -886,8 +1008,14 @@ static int run_sorted_update(int mode, const BwdWorkspace& w, int64_t n, uint32_
   const int launch_threads = gpb * G;
 #define HRB_RUN_MODE(M)                                                                                        \
   bwd_chunk_kernel<M, GradSrc><<<grid1, launch_threads, 0, st>>>(w.keys_out, w.vals_out, n, sentinel, G, src, \
-                                                                 ctx, w.partial, w.pkey, w.pflag);            \
+                                                                 ctx, w.partial, w.pkey, w.pflag, hot);       \
   HRB_LAUNCH_CHECK();                                                                                          \
+  if (hot.n_keys > 0) {                                                                                        \
+    bwd_hot_slice_kernel<GradSrc><<<hot.n_keys * HOT_SLICES, launch_threads, 0, st>>>(w.keys_out, w.vals_out, n, G, src, hot, w.hot_partial); \
+    HRB_LAUNCH_CHECK();                                                                                        \
+    bwd_hot_apply_kernel<M><<<(hot.n_keys + gpb - 1) / gpb, launch_threads, 0, st>>>(hot.n_keys, G, ctx, hot, w.hot_partial); \
+    HRB_LAUNCH_CHECK();                                                                                        \
+  }                                                                                                            \
   bwd_merge_kernel<M><<<grid2, launch_threads, 0, st>>>(n_chunks, G, ctx, w.partial, w.pkey, w.pflag);         \
   HRB_LAUNCH_CHECK();
   if (mode == 0) {
@@ -1005,16 +1133,29 @@ HRB_API int hrb_plan_create(const hrb_table_desc* tables_host, int32_t n_tables,
   }
   if (!p->uniform_dim) p->contiguous_out = false;
   p->out_chunks = (int32_t)chunk_field.size();
-  // one device blob: fields | tables | chunk_field | chunk_q | pos_field
+  // tiny tables: their rows are reduced by bwd_hot_kernel (one CTA per row)
+  std::vector<uint32_t> hot_keys;
+  for (int t = 0; t < n_tables && (int)p->hot_lo.size() < 32; ++t) {
+    const TableDev& td = p->tdev_host[t];
+    if (td.rows <= 128) {
+      p->hot_lo.push_back(td.key_base);
+      p->hot_len.push_back((uint32_t)td.rows);
+      for (int64_t r = 0; r < td.rows; ++r) hot_keys.push_back(td.key_base + (uint32_t)r);
+    }
+  }
+  p->n_hot_keys = (int32_t)hot_keys.size();
+  // one device blob: fields | tables | chunk_field | chunk_q | pos_field | hot_keys
   const size_t sz_f = align_up(sizeof(FieldDev) * n_fields), sz_t = align_up(sizeof(TableDev) * n_tables);
   const size_t sz_c = align_up(sizeof(int32_t) * chunk_field.size()), sz_p = align_up(sizeof(int32_t) * pos_field.size());
-  const size_t total = sz_f + sz_t + 2 * sz_c + sz_p;
+  const size_t sz_h = align_up(sizeof(uint32_t) * (hot_keys.size() + 1));
+  const size_t total = sz_f + sz_t + 2 * sz_c + sz_p + sz_h;
   std::vector<char> blob(total, 0);
   memcpy(blob.data(), p->fdev_host.data(), sizeof(FieldDev) * n_fields);
   memcpy(blob.data() + sz_f, p->tdev_host.data(), sizeof(TableDev) * n_tables);
   memcpy(blob.data() + sz_f + sz_t, chunk_field.data(), sizeof(int32_t) * chunk_field.size());
   memcpy(blob.data() + sz_f + sz_t + sz_c, chunk_q.data(), sizeof(int32_t) * chunk_q.size());
   memcpy(blob.data() + sz_f + sz_t + 2 * sz_c, pos_field.data(), sizeof(int32_t) * pos_field.size());
+  if (!hot_keys.empty()) memcpy(blob.data() + sz_f + sz_t + 2 * sz_c + sz_p, hot_keys.data(), sizeof(uint32_t) * hot_keys.size());
   cudaError_t e = cudaMalloc(&p->dev_blob, total);
   if (e == cudaSuccess) e = cudaMemcpy(p->dev_blob, blob.data(), total, cudaMemcpyHostToDevice);
   if (e != cudaSuccess) {
@@ -1028,6 +1169,7 @@ HRB_API int hrb_plan_create(const hrb_table_desc* tables_host, int32_t n_tables,
   p->d_chunk_field = (int32_t*)(d + sz_f + sz_t);
   p->d_chunk_q = (int32_t*)(d + sz_f + sz_t + sz_c);
   p->d_pos_field = (int32_t*)(d + sz_f + sz_t + 2 * sz_c);
+  p->d_hot_keys = (uint32_t*)(d + sz_f + sz_t + 2 * sz_c + sz_p);
   *plan_out = p;
   return HRB_OK;
 }
@@ -1201,7 +1343,7 @@ HRB_API int hrb_lookup_bwd_update(const hrb_plan* plan, const int32_t* ids, int6
   ApplyCtx ctx{plan->d_tables, plan->n_tables, *opt_host, nullptr, 0.f};
   if (opt_host->opt == HRB_OPT_ADAM_LAZY)
     ctx.lr_t = opt_host->lr * sqrtf(opt_host->bias_corr2) / opt_host->bias_corr1;
-  return run_sorted_update(opt_host->opt == HRB_OPT_SGD ? 0 : 1, w, n, sentinel, plan->key_bits, G, src, ctx, st);
+  return run_sorted_update(opt_host->opt == HRB_OPT_SGD ? 0 : 1, w, n, sentinel, plan->key_bits, G, src, ctx, hot_from_plan(plan), st);
 }
 
 HRB_API int hrb_embedding_bwd_dense_workspace(int64_t n_ids, int32_t dim, size_t* bytes) {
@@ -1241,7 +1383,15 @@ HRB_API int hrb_embedding_bwd_dense(const int32_t* ids, int64_t n_ids, const flo
   HRB_LAUNCH_CHECK();
   FlatGrad src{dout, dim};
   ApplyCtx ctx{d_t, 1, hrb_opt_params{}, dtable, 0.f};
-  return run_sorted_update(2, w, n_ids, sentinel, key_bits, dim / 4, src, ctx, st);
+  HotInfo hot{};
+  if (vocab <= HOT_MAX_ROWS) {  // the whole (tiny) table goes through the one-CTA-per-row kernel
+    hot.n_ranges = 1;
+    hot.lo[0] = 0;
+    hot.len[0] = (uint32_t)vocab;
+    hot.keys = nullptr;
+    hot.n_keys = (int32_t)vocab;
+  }
+  return run_sorted_update(2, w, n_ids, sentinel, key_bits, dim / 4, src, ctx, hot, st);
 }
 
 HRB_API int hrb_shard_ids(const hrb_plan* plan, const int32_t* ids, int64_t ids_ld, int64_t batch, int32_t n_ranks,
@@ -1572,5 +1722,6 @@ HRB_API int hrb_keyed_bwd_update(const hrb_plan* plan, const uint32_t* keys, con
   FlatGrad src{grads, plan->max_dim};
   ApplyCtx ctx{plan->d_tables, plan->n_tables, *opt_host, nullptr, 0.f};
   if (opt_host->opt == HRB_OPT_ADAM_LAZY) ctx.lr_t = opt_host->lr * sqrtf(opt_host->bias_corr2) / opt_host->bias_corr1;
-  return run_sorted_update(opt_host->opt == HRB_OPT_SGD ? 0 : 1, w, n, (uint32_t)plan->total_rows, plan->key_bits, plan->max_dim / 4, src, ctx, st);
+  return run_sorted_update(opt_host->opt == HRB_OPT_SGD ? 0 : 1, w, n, (uint32_t)plan->total_rows, plan->key_bits, plan->max_dim / 4, src, ctx,
+                           hot_from_plan(plan), st);
 }

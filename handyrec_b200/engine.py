@@ -279,6 +279,9 @@ class DeepFMEngine:
         """Replicated dense parameters: the sharded engine all-reduces the flat gradient buffer here."""
 
     grad_scale_div = 1  # number of ranks the batch mean is taken over
+    overlap_embedding_bwd = False  # sharded engine: run the row exchange/update beside the layer-0 weight gradient
+    _side = None
+    _side_pending = False
 
     def predict_on_device(self, ids: torch.Tensor, dense: Optional[torch.Tensor]) -> torch.Tensor:
         B = ids.shape[0]
@@ -306,6 +309,33 @@ class DeepFMEngine:
         if tc_step:
             call("hrb_transpose", K._p(self.X0), B, self.K0p, self.K0p, K._p(self.X0t), B, st)
             self._mark("transpose_x0")
+        op = _lib.OptParams()
+        op.opt = _lib.OPT_SGD if self.emb_opt == "sgd" else _lib.OPT_ADAM_LAZY
+        op.lr, op.beta1, op.beta2, op.eps, op.l2_scale = self.lr, self.beta1, self.beta2, self.eps, 2.0 * self.l2_embd
+        op.bias_corr1, op.bias_corr2 = 1.0 - self.beta1 ** self.step_count, 1.0 - self.beta2 ** self.step_count
+        emb_done = [False]
+
+        def emb_part(side: bool) -> None:
+            """dX0 is complete: add the FM path, then reduce + apply the embedding-row gradients (a13).  With `side`, the
+            row exchange / update runs on a second stream while the main stream finishes the layer-0 weight gradient."""
+            emb_done[0] = True
+            emb_x = self.X0[:, self.nd_pad :]
+            emb_dx = self.dX0[:, self.nd_pad :]
+            # FM path adds dlogit * (w + S - x) into the embedding columns of dX0 (interaction.py:26-39)
+            call("hrb_fm_bwd", K._p(emb_x), self.K0p, B, self.F, self.D, K._p(self.fm_w), K._p(self.dZ[-1]), K._p(emb_dx), self.K0p, 1,
+                 K._p(self.d_fm), K._stream())
+            self._mark("fm_bwd")
+            if side and self._marks is None:
+                main = torch.cuda.current_stream()
+                if self._side is None:
+                    self._side = torch.cuda.Stream()
+                self._side.wait_stream(main)
+                with torch.cuda.stream(self._side):
+                    self._embedding_backward(ids, B, K._stream(), op)
+                self._side_pending = True
+            else:
+                self._embedding_backward(ids, B, K._stream(), op)
+
         for i in range(n - 1, -1, -1):
             x, ldx = (self.A[i - 1], self.layer_ld[i - 1]) if i > 0 else (self.X0, self.K0p)
             Kp, N = self.layer_K[i], self.units[i]
@@ -316,6 +346,18 @@ class DeepFMEngine:
                      K._p(self.dZt[i - 1]) if tc_step else None, B, K._p(self.dW[i]), K._p(self.db[i]), K._p(ws), ws.numel(), st)
                 dz, lddz = self.dZ[i - 1], self.layer_ld[i - 1]
                 self._mark(f"dense_bwd_{i}_logit")
+                continue
+            if tc_step and self.tc_layer[i] and i == 0 and self.overlap_embedding_bwd:
+                # layer 0, overlapped order: dX0 first, then the embedding exchange/update on the side stream || dW0 here
+                call("hrb_dense_bwd_x_t", K._p(dz), lddz, K._p(self.W[0]), self.layer_ld[0], B, Kp, N, None, 0, 0, K._p(self.dX0), self.K0p,
+                     None, 0, st)
+                self._mark("dense_bwd_x_0")
+                emb_part(side=True)
+                call("hrb_dense_bwd_w_t_workspace", B, Kp, N, ctypes.byref(need))
+                ws = self._dense_ws(need.value)
+                call("hrb_dense_bwd_w_t", K._p(self.X0t), B, K._p(self.dZt[0]), B, K._p(dz), lddz, B, Kp, N, K._p(self.dW[0]), self.layer_ld[0],
+                     K._p(self.db[0]), K._p(ws), ws.numel(), st)
+                self._mark("dense_bwd_w_0")
                 continue
             if tc_step and self.tc_layer[i]:
                 xt = self.At[i - 1] if i > 0 else self.X0t
@@ -348,18 +390,8 @@ class DeepFMEngine:
                 call("hrb_dense_bwd_x", K._p(dz), lddz, K._p(self.W[0]), self.layer_ld[0], B, Kp, N, None, 0, 0, K._p(self.dX0), self.K0p,
                      _lib.GEMM_FP32, st)
             self._mark(f"dense_bwd_x_{i}")
-        # FM path adds dlogit * (w + S - x) into the embedding columns of dX0 (interaction.py:26-39)
-        emb_x = self.X0[:, self.nd_pad :]
-        emb_dx = self.dX0[:, self.nd_pad :]
-        call("hrb_fm_bwd", K._p(emb_x), self.K0p, B, self.F, self.D, K._p(self.fm_w), K._p(self.dZ[-1]), K._p(emb_dx), self.K0p, 1,
-             K._p(self.d_fm), st)
-        self._mark("fm_bwd")
-        # embedding rows: sort -> segment-reduce -> update (a13)
-        op = _lib.OptParams()
-        op.opt = _lib.OPT_SGD if self.emb_opt == "sgd" else _lib.OPT_ADAM_LAZY
-        op.lr, op.beta1, op.beta2, op.eps, op.l2_scale = self.lr, self.beta1, self.beta2, self.eps, 2.0 * self.l2_embd
-        op.bias_corr1, op.bias_corr2 = 1.0 - self.beta1 ** self.step_count, 1.0 - self.beta2 ** self.step_count
-        self._embedding_backward(ids, B, st, op)
+        if not emb_done[0]:
+            emb_part(side=False)
         self._sync_dense_grads()
         # dense parameters
         segs = [(0, self.n_params, False)] if self.l2_dnn == 0.0 else self._segments
@@ -373,6 +405,9 @@ class DeepFMEngine:
             else:
                 call("hrb_sgd_step", pp(self.params), pp(self.grads), length, self.lr, l2s, st)
         self._refresh_wt()
+        if self._side_pending:  # the next step's lookup must see the updated rows
+            torch.cuda.current_stream().wait_stream(self._side)
+            self._side_pending = False
         self._mark("dense_optimizer")
 
     _dws: Optional[torch.Tensor] = None

@@ -154,6 +154,7 @@ class ShardedDeepFMEngine(DeepFMEngine):
         self.provider = CudaShardProvider(self.plan, vocabs, comm.N, self.B)
         self.exchange = RowExchange(self.provider, comm)
         self.grad_scale_div = comm.N
+        self.overlap_embedding_bwd = True
 
     def _lookup_fm_forward(self, ids, B, st):
         emb = self.X0[:, self.nd_pad :]

@@ -157,6 +157,8 @@ class ThreadComm:
         self.s, self.rank, self.N = shared, rank, shared.n
 
     def _exchange(self, pieces):
+        if pieces[0].is_cuda:  # emulated ranks share one GPU but use different streams: publish only finished data
+            torch.cuda.current_stream().synchronize()
         for dst, t in enumerate(pieces):
             self.s.slots[self.rank][dst] = t
         self.s.barrier.wait()

@@ -68,14 +68,14 @@ def test_row_exchange_cuda(dev, world, opt):
                 close(s[: ws.shape[0]], ws, 1e-4)
 
 
-@pytest.mark.parametrize("world", [2, 4])
-def test_sharded_engine_matches_single_gpu_engine(dev, world):
+@pytest.mark.parametrize("world,b", [(2, 64), (4, 64), (2, 512)])
+def test_sharded_engine_matches_single_gpu_engine(dev, world, b):
     """N emulated ranks with row-sharded tables take the same SGD step as one engine on the concatenated batch."""
     from handyrec_b200 import kernels as K
     from handyrec_b200.engine import DeepFMEngine
     from handyrec_b200.sharded import ShardedDeepFMEngine
 
-    b, D, n_dense, hidden = 64, 8, 3, (16, 1)
+    D, n_dense, hidden = 8, 3, (16, 1)  # b = 512 takes the tcgen05 path with the overlapped embedding backward
     g = torch.Generator().manual_seed(1)
     vocabs = [11, 50, 300]
     tables = [(torch.rand(v, D, generator=g) - 0.5) * 0.1 for v in vocabs]

@@ -194,3 +194,38 @@ def test_layer_face_eager_calls(dev):
     xin = torch.randn(33, 6, 8, device=dev)
     out = fm(xin)
     close(out, oracle.fm(xin.cpu(), fm.linear.detach().cpu(), fm.w_0.detach().cpu()), 1e-5)
+
+
+def test_embd_feature_group_values(dev):
+    """a12: EmbdFeatureGroup.get_embd / lookup / __call__ (features/group.py:439-516) against the oracle."""
+    from handyrec_b200.features import DenseFeature, EmbdFeatureGroup, FeaturePool, SparseFeature, SparseSeqFeature
+    from handyrec_b200.keras_lite import Input, Model
+
+    dense_feats = [DenseFeature("d1", dim=1), DenseFeature("d2", dim=2)]
+    sparse_feats = [SparseFeature("s1", vocab_size=10, embedding_dim=16), SparseFeature("s2", vocab_size=20, embedding_dim=16)]
+    seq_feats = [SparseSeqFeature(sparse_feats[0], "s2_seq", seq_len=4)]
+    value_dict = {"s1": [0, 1, 2, 3], "s2": [11, 12, 13, 14], "d1": [-1.0, -2.0, -3.0, -4.0], "d2": [[1.0, 2], [3, 4], [5, 6], [7, 8]],
+                  "s2_seq": [[0, 0, 0, 0], [5, 6, 0, 0], [6, 7, 8, 9], [0, 0, 0, 3]]}
+    fg = EmbdFeatureGroup("FG", "s1", dense_feats + sparse_feats + seq_feats, FeaturePool(), value_dict, embd_dim=8, pool_method="mean")
+    item_id = fg.id_input
+    seq_in = Input(shape=(3,), name="seq", dtype="int32")
+    full = fg.get_embd(item_id, compress=False)
+    looked = fg.lookup(seq_in, compress=False)
+    out, mask = fg(seq_in)
+    model = Model(inputs=[item_id, seq_in], outputs=[full, looked, out, mask])
+    ids = np.array([[1], [3]], dtype=np.int32)
+    seq = np.array([[1, 2, 0], [3, 0, 1]], dtype=np.int32)
+    got_full, got_looked, got_out, got_mask = model({"s1": ids, "seq": seq})
+    t1 = fg.embd_layers["s1"].embeddings.detach().cpu()
+    t2 = fg.embd_layers["s2"].embeddings.detach().cpu()
+    e_s1 = t1[torch.tensor(value_dict["s1"])]
+    e_s2 = t2[torch.tensor(value_dict["s2"])]
+    seq_e, seq_m = oracle.custom_embedding(t1, torch.tensor(value_dict["s2_seq"]), True)
+    e_seq = oracle.sequence_pooling(seq_e, seq_m, "mean")[:, 0]
+    want_full = torch.cat([torch.tensor(value_dict["d1"]).unsqueeze(-1), torch.tensor(value_dict["d2"]), e_s1, e_s2, e_seq], -1)
+    assert got_full.shape == (4, 1 + 2 + 48)
+    close(got_full, want_full, 1e-5)
+    close(got_looked, want_full[torch.from_numpy(seq).long()], 1e-5)
+    w, b = fg._output_layer.kernel.detach().cpu(), fg._output_layer.bias.detach().cpu()
+    close(got_out, (want_full @ w + b)[torch.from_numpy(seq).long()], 1e-5)
+    assert got_mask.shape == (2, 3, 8) and np.array_equal(got_mask.cpu().numpy(), np.repeat((seq != 0)[..., None], 8, -1))

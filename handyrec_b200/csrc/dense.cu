@@ -374,9 +374,10 @@ __global__ void __launch_bounds__(256) hrb_transpose_kernel(const float* __restr
 
 // implemented in gemm_tc.cu (tcgen05 3xTF32); return HRB_UNSUPPORTED when the shape is not covered
 int hrb_tc_gemm_bias_act(const float* a, int64_t lda, const float* bt, int64_t ldb, const float* bias, int64_t M, int32_t N, int32_t K,
-                         int32_t act, float* c, int64_t ldc, float* ct, int64_t ldct, cudaStream_t st);
+                         int32_t act, float* c, int64_t ldc, float* ct, int64_t ldct, uint32_t* relu_mask, int64_t mask_ld, cudaStream_t st);
 int hrb_tc_gemm_act_grad(const float* a, int64_t lda, const float* bt, int64_t ldb, int64_t M, int32_t N, int32_t K, const float* aprev,
-                         int64_t ldap, int32_t act, float* c, int64_t ldc, float* ct, int64_t ldct, cudaStream_t st);
+                         int64_t ldap, int32_t act, float* c, int64_t ldc, float* ct, int64_t ldct, const uint32_t* relu_mask, int64_t mask_ld,
+                         cudaStream_t st);
 int hrb_tc_splits(int64_t M, int32_t N, int32_t K);
 int hrb_tc_gemm_splitk(const float* a, int64_t lda, const float* bt, int64_t ldb, int64_t M, int32_t N, int32_t K, int32_t splits,
                        float* part, int64_t ldp, cudaStream_t st);
@@ -500,21 +501,22 @@ HRB_API int hrb_transpose(const float* src, int64_t rows, int32_t cols, int64_t 
 }
 
 HRB_API int hrb_dense_fwd_t(const float* x, int64_t ldx, const float* wt, int64_t ldwt, const float* bias, int64_t M, int32_t K,
-                            int32_t N, int32_t act, float* y, int64_t ldy, float* yt, int64_t ldyt, void* stream) {
+                            int32_t N, int32_t act, float* y, int64_t ldy, float* yt, int64_t ldyt, uint32_t* relu_mask, void* stream) {
   HRB_REQUIRE(x && wt && y && M >= 0 && K > 0 && N > 0 && ldx >= K && ldwt >= K && ldy >= N, "hrb_dense_fwd_t: bad argument");
   HRB_REQUIRE(yt == nullptr || ldyt >= M, "hrb_dense_fwd_t: ldyt < M");
   HRB_REQUIRE(act >= HRB_ACT_LINEAR && act <= HRB_ACT_TANH, "hrb_dense_fwd_t: unknown activation %d", act);
   if (M == 0) return HRB_OK;
-  return hrb_tc_gemm_bias_act(x, ldx, wt, ldwt, bias, M, N, K, act, y, ldy, yt, ldyt, (cudaStream_t)stream);
+  return hrb_tc_gemm_bias_act(x, ldx, wt, ldwt, bias, M, N, K, act, y, ldy, yt, ldyt, relu_mask, (N + 31) / 32, (cudaStream_t)stream);
 }
 
 HRB_API int hrb_dense_bwd_x_t(const float* dz, int64_t lddz, const float* w, int64_t ldw, int64_t M, int32_t K, int32_t N,
-                              const float* a_prev, int64_t lda_prev, int32_t act_prev, float* dx, int64_t lddx, float* dxt,
-                              int64_t lddxt, void* stream) {
+                              const float* a_prev, int64_t lda_prev, int32_t act_prev, const uint32_t* relu_mask, float* dx, int64_t lddx,
+                              float* dxt, int64_t lddxt, void* stream) {
   HRB_REQUIRE(dz && w && dx && M >= 0 && K > 0 && N > 0 && lddz >= N && ldw >= N && lddx >= K, "hrb_dense_bwd_x_t: bad argument");
   HRB_REQUIRE(dxt == nullptr || lddxt >= M, "hrb_dense_bwd_x_t: lddxt < M");
   if (M == 0) return HRB_OK;
-  return hrb_tc_gemm_act_grad(dz, lddz, w, ldw, M, K, N, a_prev, lda_prev, act_prev, dx, lddx, dxt, lddxt, (cudaStream_t)stream);
+  return hrb_tc_gemm_act_grad(dz, lddz, w, ldw, M, K, N, a_prev, lda_prev, act_prev, dx, lddx, dxt, lddxt, relu_mask, (K + 31) / 32,
+                              (cudaStream_t)stream);
 }
 
 HRB_API int hrb_dense_bwd_w_t_workspace(int64_t M, int32_t K, int32_t N, size_t* bytes) {

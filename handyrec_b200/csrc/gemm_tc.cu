@@ -112,6 +112,9 @@ struct Args {
   int32_t act;
   int32_t splits;      // split over K (EPI_PLAIN): slice z writes C + z*M*ldc
   int32_t kb_per_split;
+  uint32_t* mask_out;  // EPI_BIAS_ACT + relu: bit j of word [m][n0/32] = (y[m][n0+j] > 0), for the backward
+  const uint32_t* mask_in;  // EPI_ACT_GRAD + relu: the same words instead of re-reading the activations
+  int64_t mask_ld;     // words per row
   int32_t debug;       // HRB_TC_DEBUG bit mask (perf experiments only): 1 no stores, 2 no conversion, 4 no MMA, 8 no TMA
 };
 
@@ -303,12 +306,22 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
           if (g.act == HRB_ACT_RELU) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+            if (g.mask_out != nullptr && row_ok) {
+              uint32_t word = 0;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) word |= (v[j] > 0.f ? 1u : 0u) << j;
+              g.mask_out[m * g.mask_ld + (n0 >> 5)] = word;
+            }
           } else if (g.act != HRB_ACT_LINEAR) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = act_apply(g.act, v[j]);
           }
         } else if (EPI == EPI_ACT_GRAD) {
-          if (g.aprev != nullptr && row_ok) {
+          if (g.mask_in != nullptr && g.act == HRB_ACT_RELU) {
+            const uint32_t word = row_ok ? __ldg(g.mask_in + m * g.mask_ld + (n0 >> 5)) : 0u;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = ((word >> j) & 1u) ? v[j] : 0.f;
+          } else if (g.aprev != nullptr && row_ok) {
             const float* ap = g.aprev + m * g.ldap + n0;
 #pragma unroll
             for (int j4 = 0; j4 < 32; j4 += 4) {
@@ -457,19 +470,20 @@ using namespace hrb;
 // Internal entry points (exported through dense.cu): all operands "TN" = reduction dim contiguous.
 // C[M,N] = act(A[M,K] * Bt[N,K]^T + bias)  (+ transposed copy Ct[N,M])
 int hrb_tc_gemm_bias_act(const float* a, int64_t lda, const float* bt, int64_t ldb, const float* bias, int64_t M, int32_t N, int32_t K,
-                         int32_t act, float* c, int64_t ldc, float* ct, int64_t ldct, cudaStream_t st) {
+                         int32_t act, float* c, int64_t ldc, float* ct, int64_t ldct, uint32_t* relu_mask, int64_t mask_ld, cudaStream_t st) {
   if (!tc::tc_ok(a, lda, bt, ldb, M, N, K) || !aligned16(c) || ldc % 4 != 0 || (ct != nullptr && (!aligned16(ct) || ldct % 4 != 0)))
     return fail(HRB_UNSUPPORTED, "tcgen05 GEMM: shape/alignment not covered");
-  tc::Args g{c, ct, bias, nullptr, ldc, ldct, 0, M, N, K, act, 1, (K + tc::BK - 1) / tc::BK};
+  tc::Args g{c, ct, bias, nullptr, ldc, ldct, 0, M, N, K, act, 1, (K + tc::BK - 1) / tc::BK, relu_mask, nullptr, mask_ld, 0};
   return tc::launch<128, tc::EPI_BIAS_ACT>(a, lda, bt, ldb, g, st);
 }
 // C[M,N] = (A[M,K] * Bt[N,K]^T) * act'(aprev[M,N])  (+ transposed copy)
 int hrb_tc_gemm_act_grad(const float* a, int64_t lda, const float* bt, int64_t ldb, int64_t M, int32_t N, int32_t K, const float* aprev,
-                         int64_t ldap, int32_t act, float* c, int64_t ldc, float* ct, int64_t ldct, cudaStream_t st) {
+                         int64_t ldap, int32_t act, float* c, int64_t ldc, float* ct, int64_t ldct, const uint32_t* relu_mask, int64_t mask_ld,
+                         cudaStream_t st) {
   if (!tc::tc_ok(a, lda, bt, ldb, M, N, K) || !aligned16(c) || ldc % 4 != 0 || (aprev != nullptr && (!aligned16(aprev) || ldap % 4 != 0)) ||
       (ct != nullptr && (!aligned16(ct) || ldct % 4 != 0)))
     return fail(HRB_UNSUPPORTED, "tcgen05 GEMM: shape/alignment not covered");
-  tc::Args g{c, ct, nullptr, aprev, ldc, ldct, ldap, M, N, K, act, 1, (K + tc::BK - 1) / tc::BK};
+  tc::Args g{c, ct, nullptr, aprev, ldc, ldct, ldap, M, N, K, act, 1, (K + tc::BK - 1) / tc::BK, nullptr, relu_mask, mask_ld, 0};
   return tc::launch<128, tc::EPI_ACT_GRAD>(a, lda, bt, ldb, g, st);
 }
 // split-K partials: part[z][M][ldp] = A[M, Kz] * Bt[N, Kz]^T ; the caller reduces over z in fixed order
@@ -489,7 +503,7 @@ int hrb_tc_gemm_splitk(const float* a, int64_t lda, const float* bt, int64_t ldb
   const int kb_total = (K + tc::BK - 1) / tc::BK;
   const int per = (kb_total + splits - 1) / splits;
   if ((kb_total + per - 1) / per != splits) return fail(HRB_BAD_ARG, "tcgen05 split-K GEMM: %d splits leave empty slices", splits);
-  tc::Args g{part, nullptr, nullptr, nullptr, ldp, 0, 0, M, N, K, 0, splits, per};
+  tc::Args g{part, nullptr, nullptr, nullptr, ldp, 0, 0, M, N, K, 0, splits, per, nullptr, nullptr, 0, 0};
   return tc::launch<128, tc::EPI_PLAIN>(a, lda, bt, ldb, g, st);
 }
 
@@ -506,7 +520,7 @@ int hrb_tc_dense_bwd_x(const float* dz, int64_t lddz, const float* w, int64_t ld
   if (!tc::tc_ok(dz, lddz, w, ldw, M, K, N)) return hrb::fail(HRB_UNSUPPORTED, "tcgen05 bwd_x: shape/alignment not covered");
   if (a_prev != nullptr && !(aligned16(a_prev) && lda_prev % 4 == 0)) return hrb::fail(HRB_UNSUPPORTED, "tcgen05 bwd_x: a_prev alignment");
   if (!(aligned16(dx) && lddx % 4 == 0)) return hrb::fail(HRB_UNSUPPORTED, "tcgen05 bwd_x: dx alignment");
-  tc::Args g{dx, nullptr, nullptr, a_prev, lddx, 0, lda_prev, M, K, N, act_prev, 1, (N + tc::BK - 1) / tc::BK};
+  tc::Args g{dx, nullptr, nullptr, a_prev, lddx, 0, lda_prev, M, K, N, act_prev, 1, (N + tc::BK - 1) / tc::BK, nullptr, nullptr, 0, 0};
   return tc::launch<128, tc::EPI_ACT_GRAD>(dz, lddz, w, ldw, g, st);
 }
 int hrb_tc_dense_bwd_w(const float*, int64_t, const float*, int64_t, int64_t, int32_t, int32_t, float*, int64_t, void*, size_t,

@@ -154,6 +154,8 @@ class DeepFMEngine:
             self.X0t = torch.zeros(self.K0p, B, **f32)
             self.At = [torch.zeros(ld, B, **f32) for ld in self.layer_ld]
             self.dZt = [torch.zeros(ld, B, **f32) for ld in self.layer_ld]
+            # relu sign bits of every hidden activation (1 bit/element) for the activation-gradient epilogue
+            self.relu_mask = [torch.zeros(B, (u + 31) // 32, device=self.dev, dtype=torch.int32) if self.act == "relu" else None for u in self.units]
             self._refresh_wt()
         self.ids_dev = torch.zeros(B, self.ids_cols, device=self.dev, dtype=torch.int32)
         self.dense_dev = torch.zeros(B, max(self.n_dense, 1), **f32)
@@ -254,7 +256,8 @@ class DeepFMEngine:
                 call("hrb_dense1_fwd", K._p(x), ldx, K._p(self.W[i]), K._p(self.b[i]), B, self.layer_K[i], K._p(self.A[i]), st)
             elif self.use_tc and self.tc_layer[i] and B == self.B:
                 call("hrb_dense_fwd_t", K._p(x), ldx, K._p(self.Wt[i]), self.layer_K[i], K._p(self.b[i]), B, self.layer_K[i], self.units[i],
-                     _lib.ACT[act], K._p(self.A[i]), self.layer_ld[i], K._p(self.At[i]) if training else None, B, st)
+                     _lib.ACT[act], K._p(self.A[i]), self.layer_ld[i], K._p(self.At[i]) if training else None, B,
+                     K._p(self.relu_mask[i]) if (training and act == "relu") else None, st)
             else:
                 call("hrb_dense_fwd", K._p(x), ldx, K._p(self.W[i]), self.layer_ld[i], K._p(self.b[i]), B, self.layer_K[i], self.units[i],
                      _lib.ACT[act], K._p(self.A[i]), self.layer_ld[i], _lib.GEMM_FP32, st)
@@ -349,7 +352,7 @@ class DeepFMEngine:
                 continue
             if tc_step and self.tc_layer[i] and i == 0 and self.overlap_embedding_bwd:
                 # layer 0, overlapped order: dX0 first, then the embedding exchange/update on the side stream || dW0 here
-                call("hrb_dense_bwd_x_t", K._p(dz), lddz, K._p(self.W[0]), self.layer_ld[0], B, Kp, N, None, 0, 0, K._p(self.dX0), self.K0p,
+                call("hrb_dense_bwd_x_t", K._p(dz), lddz, K._p(self.W[0]), self.layer_ld[0], B, Kp, N, None, 0, 0, None, K._p(self.dX0), self.K0p,
                      None, 0, st)
                 self._mark("dense_bwd_x_0")
                 emb_part(side=True)
@@ -367,11 +370,13 @@ class DeepFMEngine:
                      K._p(self.db[i]), K._p(ws), ws.numel(), st)
                 self._mark(f"dense_bwd_w_{i}")
                 if i > 0:
+                    use_mask = self.act == "relu" and self.tc_layer[i - 1]  # the mask was written by the tensor-core forward of layer i-1
                     call("hrb_dense_bwd_x_t", K._p(dz), lddz, K._p(self.W[i]), self.layer_ld[i], B, Kp, N, K._p(self.A[i - 1]), self.layer_ld[i - 1],
-                         _lib.ACT[self.act], K._p(self.dZ[i - 1]), self.layer_ld[i - 1], K._p(self.dZt[i - 1]), B, st)
+                         _lib.ACT[self.act], K._p(self.relu_mask[i - 1]) if use_mask else None, K._p(self.dZ[i - 1]), self.layer_ld[i - 1],
+                         K._p(self.dZt[i - 1]), B, st)
                     dz, lddz = self.dZ[i - 1], self.layer_ld[i - 1]
                 else:
-                    call("hrb_dense_bwd_x_t", K._p(dz), lddz, K._p(self.W[0]), self.layer_ld[0], B, Kp, N, None, 0, 0, K._p(self.dX0), self.K0p,
+                    call("hrb_dense_bwd_x_t", K._p(dz), lddz, K._p(self.W[0]), self.layer_ld[0], B, Kp, N, None, 0, 0, None, K._p(self.dX0), self.K0p,
                          None, 0, st)
                 self._mark(f"dense_bwd_x_{i}")
                 continue

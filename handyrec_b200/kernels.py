@@ -396,25 +396,25 @@ def transpose(src: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Te
     return out
 
 
-def dense_fwd_t(x, wt, bias, act=None, out=None, out_t=None):
+def dense_fwd_t(x, wt, bias, act=None, out=None, out_t=None, relu_mask=None):
     """y = act(x @ wt.T + bias); wt is (N, K).  out_t (N, M) optionally receives y^T."""
     M, Kd = x.shape
     N = wt.shape[0]
     if out is None:
         out = torch.empty(M, N, device=x.device, dtype=torch.float32)
     call("hrb_dense_fwd_t", _p(x), _row_major_2d(x, "x"), _p(wt), _row_major_2d(wt, "wt"), _p(bias), M, Kd, N, ACT[act], _p(out),
-         _row_major_2d(out, "out"), _p(out_t), _row_major_2d(out_t, "out_t") if out_t is not None else 0, _stream())
+         _row_major_2d(out, "out"), _p(out_t), _row_major_2d(out_t, "out_t") if out_t is not None else 0, _p(relu_mask), _stream())
     return out
 
 
-def dense_bwd_x_t(dz, w, a_prev=None, act_prev=None, out=None, out_t=None):
+def dense_bwd_x_t(dz, w, a_prev=None, act_prev=None, out=None, out_t=None, relu_mask=None):
     """dx = (dz @ w.T) * act'(a_prev); w is (K, N) row-major as in the forward."""
     M, N = dz.shape
     Kd = w.shape[0]
     if out is None:
         out = torch.empty(M, Kd, device=dz.device, dtype=torch.float32)
     call("hrb_dense_bwd_x_t", _p(dz), _row_major_2d(dz, "dz"), _p(w), _row_major_2d(w, "w"), M, Kd, N, _p(a_prev),
-         _row_major_2d(a_prev, "a_prev") if a_prev is not None else 0, ACT[act_prev], _p(out), _row_major_2d(out, "out"), _p(out_t),
+         _row_major_2d(a_prev, "a_prev") if a_prev is not None else 0, ACT[act_prev], _p(relu_mask), _p(out), _row_major_2d(out, "out"), _p(out_t),
          _row_major_2d(out_t, "out_t") if out_t is not None else 0, _stream())
     return out
 

@@ -189,11 +189,13 @@ int hrb_dense_bwd_w(const float* x, int64_t ldx, const float* dz, int64_t lddz, 
  * dzt[N,M] for the weight gradient.  yt / dxt (nullable) receive the transposed copy of the output for the
  * next weight gradient.  Shapes the tensor-core kernel does not cover return HRB_UNSUPPORTED (use hrb_dense_*). */
 int hrb_transpose(const float* src, int64_t rows, int32_t cols, int64_t lds, float* dst, int64_t ldd, void* stream);
+/* relu_mask (nullable): uint32 words [M][ceil(units/32)], bit j of word [m][c] = (activation[m][32c+j] > 0).  The relu
+ * forward writes it; the backward of the layer above reads it instead of re-reading the activations (a_prev is then unused). */
 int hrb_dense_fwd_t(const float* x, int64_t ldx, const float* wt, int64_t ldwt, const float* bias, int64_t M, int32_t K,
-                    int32_t N, int32_t act, float* y, int64_t ldy, float* yt, int64_t ldyt, void* stream);
+                    int32_t N, int32_t act, float* y, int64_t ldy, float* yt, int64_t ldyt, uint32_t* relu_mask, void* stream);
 int hrb_dense_bwd_x_t(const float* dz, int64_t lddz, const float* w, int64_t ldw, int64_t M, int32_t K, int32_t N,
-                      const float* a_prev, int64_t lda_prev, int32_t act_prev, float* dx, int64_t lddx, float* dxt,
-                      int64_t lddxt, void* stream);
+                      const float* a_prev, int64_t lda_prev, int32_t act_prev, const uint32_t* relu_mask, float* dx, int64_t lddx,
+                      float* dxt, int64_t lddxt, void* stream);
 int hrb_dense_bwd_w_t_workspace(int64_t M, int32_t K, int32_t N, size_t* bytes);
 int hrb_dense_bwd_w_t(const float* xt, int64_t ldxt, const float* dzt, int64_t lddzt, const float* dz, int64_t lddz, int64_t M,
                       int32_t K, int32_t N, float* dw, int64_t lddw, float* dbias, void* workspace, size_t workspace_bytes,

@@ -110,3 +110,23 @@ def test_dense1_logit_layer(dev, M, Kd, act):
     close(dzt, want.float().t(), 1e-4)
     close(dw, (xa.double().T @ dy.double()).float(), 1e-4)
     close(db, dy.double().sum().float().reshape(1), 1e-4)
+
+
+def test_relu_sign_mask_round_trip(dev):
+    """The forward's relu sign bits drive the activation-gradient epilogue exactly like re-reading the activations."""
+    k = K()
+    M, Kd, N = 2048, 128, 429
+    x = rnd(M, Kd, seed=1).to(dev)
+    wt = (rnd(N, Kd, seed=2) / 10).to(dev)
+    ldn = (N + 3) // 4 * 4
+    a = torch.zeros(M, ldn, device=dev)
+    mask = torch.zeros(M, (N + 31) // 32, device=dev, dtype=torch.int32)
+    k.dense_fwd_t(x, wt, None, "relu", out=a[:, :N], relu_mask=mask)
+    bits = (mask.cpu().numpy().astype(np.uint32)[:, :, None] >> np.arange(32, dtype=np.uint32)) & 1
+    assert np.array_equal(bits.reshape(M, -1)[:, :N].astype(bool), (a[:, :N] > 0).cpu().numpy())
+    # layer above: dz (M, 64) through w (N, 64) back to (M, N), masked by relu'(a)
+    dz = rnd(M, 64, seed=3).to(dev)
+    w = (rnd(N, 64, seed=4) / 8).to(dev)
+    ref = k.dense_bwd_x_t(dz, w, a_prev=a[:, :N], act_prev="relu", out=torch.zeros(M, ldn, device=dev)[:, :N])
+    got = k.dense_bwd_x_t(dz, w, act_prev="relu", relu_mask=mask, out=torch.zeros(M, ldn, device=dev)[:, :N])
+    assert torch.equal(ref, got)

@@ -804,7 +804,7 @@ __global__ void __launch_bounds__(256) bwd_hot_apply_kernel(int n_rows, int G, A
 // Step 3: chunk kernel.  G lanes own CH consecutive sorted positions.  Runs (equal keys) that lie
 // strictly inside the chunk are final and update their row at once; the (at most two) runs that
 // touch a chunk edge and continue across it go to the partial buffer (slot 0 = head, 1 = tail).
-constexpr int CH = 16;
+constexpr int CH = 8;
 constexpr uint32_t PF_VALID = 1u, PF_CONT = 2u, PF_ROPEN = 4u;
 
 template <int MODE, typename GradSrc>

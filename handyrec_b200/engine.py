@@ -437,6 +437,58 @@ class DeepFMEngine:
         torch.cuda.current_stream().synchronize()
         return float(self.loss_host[0]) / B
 
+    def fit_batches(self, batches) -> List[float]:
+        """Keras-`fit`-like loop over host batches `(ids, dense, label)` (pinned tensors) with input prefetch:
+        the H2D copies of batch t+1 run on a copy stream while batch t computes, and every step's loss is copied
+        back asynchronously; the host waits once, at the end.  Returns the per-step mean losses."""
+        main = torch.cuda.current_stream()
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream()
+            f32 = dict(device=self.dev, dtype=torch.float32)
+            self._stage = [(torch.zeros(self.B, self.ids_cols, device=self.dev, dtype=torch.int32), torch.zeros(self.B, max(self.n_dense, 1), **f32),
+                            torch.zeros(self.B, **f32)) for _ in range(2)]
+            self._stage_ready = [torch.cuda.Event(), torch.cuda.Event()]
+            self._stage_free = [torch.cuda.Event(), torch.cuda.Event()]
+        it = iter(batches)
+        losses_host: List[torch.Tensor] = []
+        sizes: List[int] = []
+
+        def upload(slot, batch):
+            ids_h, dense_h, label_h = batch
+            B = ids_h.shape[0]
+            with torch.cuda.stream(self._copy_stream):
+                self._copy_stream.wait_event(self._stage_free[slot])  # the previous user of this slot has finished
+                ids_d, dense_d, label_d = self._stage[slot]
+                ids_d[:B].copy_(ids_h, non_blocking=True)
+                if self.n_dense:
+                    dense_d[:B].copy_(dense_h, non_blocking=True)
+                label_d[:B].copy_(label_h, non_blocking=True)
+                self._stage_ready[slot].record(self._copy_stream)
+            return B
+
+        for e in self._stage_free:
+            e.record(main)
+        nxt = next(it, None)
+        slot = 0
+        if nxt is not None:
+            nB = upload(slot, nxt)
+        while nxt is not None:
+            cur_slot, B = slot, nB
+            nxt = next(it, None)
+            if nxt is not None:
+                slot ^= 1
+                nB = upload(slot, nxt)
+            main.wait_event(self._stage_ready[cur_slot])
+            ids_d, dense_d, label_d = self._stage[cur_slot]
+            self.train_step_on_device(ids_d[:B], dense_d[:B] if self.n_dense else None, label_d[:B])
+            self._stage_free[cur_slot].record(main)
+            lh = torch.empty(1, dtype=torch.float32).pin_memory()
+            lh.copy_(self.loss_sum, non_blocking=True)  # D2H of this step's loss, not waited for here
+            losses_host.append(lh)
+            sizes.append(B)
+        main.synchronize()
+        return [float(l[0]) / b for l, b in zip(losses_host, sizes)]
+
     def predict(self, ids_host: torch.Tensor, dense_host: Optional[torch.Tensor]) -> torch.Tensor:
         B = ids_host.shape[0]
         self.ids_dev[:B].copy_(ids_host, non_blocking=True)

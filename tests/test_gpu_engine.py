@@ -101,3 +101,20 @@ def test_engine_rejects_bad_configs(dev):
         DeepFMEngine(t, [(0, 1, "none")], 0, (8, 4))
     with pytest.raises(ValueError):
         DeepFMEngine([torch.zeros(10, 8, device=dev), torch.zeros(10, 16, device=dev)], [(0, 1, "none"), (1, 1, "none")], 0, (8, 1))
+
+
+def test_fit_batches_equals_blocking_calls(dev):
+    B, D, n_dense, hidden = 96, 8, 2, (8, 1)
+    eng_a, tables, fields, ids, dense, label = _setup(dev, B, D, n_dense, hidden, "sgd")
+    eng_b, *_ = _setup(dev, B, D, n_dense, hidden, "sgd")
+    g = torch.Generator().manual_seed(9)
+    batches = []
+    for t in range(5):
+        perm = torch.randperm(B, generator=g)
+        batches.append((ids[perm].contiguous().pin_memory(), dense[perm].contiguous().pin_memory(), label[perm].contiguous().pin_memory()))
+    want = [eng_a.train_on_batch(*b) for b in batches]
+    got = eng_b.fit_batches(batches)
+    assert len(got) == 5 and all(abs(a - b) <= 1e-6 * max(1.0, abs(a)) for a, b in zip(want, got))
+    for ta, tb in zip(eng_a.tables, eng_b.tables):
+        assert torch.equal(ta, tb)
+    assert torch.equal(eng_a.params, eng_b.params)

@@ -308,26 +308,31 @@ def main():
         flops[f"dense_bwd_x_{i}"] = f
     lookup_bytes = LOOKUP_BYTES_PER_SAMPLE * B
 
-    def roofline_for(name, dur_ms, peak_kind):
-        if name in flops:
-            ach = flops[name] / (dur_ms * 1e-3) / 1e12
-            peak = peaks["bf16_tflops_sustained"]
-            return {"kernel": name, "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
-                    "peak_source": f"{peaks['source']} bf16 sustained; fp32-parity path, see DESIGN.md"}
-        ach = lookup_bytes / (dur_ms * 1e-3) / 1e9
-        peak = peaks["hbm_gbs"]
-        return {"kernel": name, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
-                "peak_source": f"{peaks['source']} copy bandwidth ({peak_kind})"}
-
+    # dominant kernel = the tcgen05 GEMM kernel (one kernel, 9 launches per step: 3 fwd, 3 bwd_x, 3 split-K bwd_w)
+    gemm_names = [k for k in phases if k in flops and not k.endswith("_3")]
+    gemm_ms = sum(phases[k] for k in gemm_names)
+    gemm_flops = sum(flops[k] for k in gemm_names)
+    ach = gemm_flops / (gemm_ms * 1e-3) / 1e12
+    roofline = {"kernel": "tc::gemm_tc_kernel (tcgen05 3xTF32, %d launches/step; bwd_w phases include their split-reduce/colsum kernels)" % len(gemm_names),
+                "bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": ach / peaks["bf16_tflops_sustained"],
+                "traffic": None, "share_of_step": gemm_ms / total_phase, "flops_per_step": gemm_flops,
+                "peak_source": f"{peaks['source']} bf16 sustained (kernel timed inside a long step)",
+                "note": "fp32 parity needs 3 TF32 MMAs per product at half the bf16 rate: ceiling of this scheme = 1/6 = 0.167 of the bf16 peak (DESIGN.md 3); ncu tensor-pipe active 34-48% (profiles/r01_ncu_full_summary.md)"}
     lk = "lookup_fm_fwd" if world == 1 else "sharded_lookup_fwd"
-    roofline = roofline_for(dom, phases[dom], "sustained") if dom in flops or dom == lk else {
-        "kernel": dom, "bound": "hbm", "achieved": None, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": None, "traffic": None}
-    roofline["share_of_step"] = phases[dom] / total_phase
-    rl_lookup = roofline_for(lk, phases[lk], "in-step")
-    rl_lookup["alone_ms"] = lookup_alone_ms
-    rl_lookup["alone_achieved"] = lookup_bytes / (lookup_alone_ms * 1e-3) / 1e9
-    rl_lookup["alone_frac"] = rl_lookup["alone_achieved"] / peaks["hbm_gbs"]
-    rl_lookup["bytes_per_sample"] = LOOKUP_BYTES_PER_SAMPLE
+    lk_ach = lookup_bytes / (phases[lk] * 1e-3) / 1e9
+    rl_lookup = {"kernel": "hrb::lookup_tile_kernel (fused lookup + FM)" if world == 1 else "row exchange (route + all-to-all + gather + scatter)",
+                 "bound": "hbm", "achieved": lk_ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": lk_ach / peaks["hbm_gbs"],
+                 "traffic": 159.0e6 if world == 1 else None, "traffic_note": "dram read+write per launch from profiles/r01_ncu_full_summary.md",
+                 "peak_source": f"{peaks['source']} copy bandwidth", "bytes_per_sample": LOOKUP_BYTES_PER_SAMPLE, "in_step_ms": phases[lk],
+                 "alone_ms": lookup_alone_ms, "alone_achieved": lookup_bytes / (lookup_alone_ms * 1e-3) / 1e9,
+                 "alone_frac": lookup_bytes / (lookup_alone_ms * 1e-3) / 1e9 / peaks["hbm_gbs"]}
+    eb = "embedding_bwd_update" if world == 1 else "sharded_embedding_bwd_update"
+    uniq = int(sum(torch.unique(ids_pool[0][:, f]).numel() for f in range(len(vocabs))))
+    S = 3 if eng.emb_opt == "adam_lazy" else 1
+    eb_bytes = B * len(vocabs) * (4 + EMB_DIM * 4) + uniq * EMB_DIM * 4 * 2 * S
+    eb_ach = eb_bytes / (phases[eb] * 1e-3) / 1e9
+    rl_emb = {"kernel": "bwd_keys + radix sort + bwd_chunk/hot/merge (a13)", "bound": "hbm", "achieved": eb_ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+              "frac": eb_ach / peaks["hbm_gbs"], "unique_rows": uniq, "bytes_per_step": eb_bytes, "in_step_ms": phases[eb]}
 
     cpu = None
     if not args.no_cpu_baseline:
@@ -347,7 +352,7 @@ def main():
                 "ms_per_step": e2e_ms / args.steps, "last_loss": loss, "api": "DeepFMEngine.fit_batches (pinned host batches, prefetching copy stream, async loss read-back every step)",
                 "blocking_train_on_batch_samples_per_s": B * world * args.steps / (e2e_sync_ms * 1e-3)},
         "gpu_launches": launches, "gpu_launches_per_step": launches / max(args.steps, 1),
-        "clocks": clk, "roofline": roofline, "roofline_lookup": rl_lookup, "cpu_baseline": cpu,
+        "clocks": clk, "roofline": roofline, "roofline_lookup": rl_lookup, "roofline_embedding_bwd": rl_emb, "cpu_baseline": cpu,
         "kernel_ms": {k: round(v, 4) for k, v in phases.items()},
     }
     print(json.dumps(line), flush=True)

@@ -4,8 +4,9 @@
 //   C[M,N] = A[M,K] * Bt[N,K]^T      A, Bt row-major with the reduction dim contiguous ("K-major")
 //
 // fp32 parity (<= 1e-5 forward, <= 1e-4 gradients) rules out plain TF32 (10-bit mantissa).  Every fp32
-// operand tile is split in shared memory into hi = x & 0xFFFFE000 (exactly representable in TF32) and
-// lo = x - hi, and three MMAs accumulate hi*hi + lo*hi + hi*lo in TMEM (fp32): error ~2^-21, like FFMA.
+// operand tile is split into hi = x & 0xFFFFE000 (what kind::tf32 reads of a raw fp32 word -- the low 13 mantissa
+// bits are ignored, verified against explicit masking) and lo = x - hi (written to a second smem tile), and three
+// MMAs accumulate lo*hi + hi*lo + hi*hi in TMEM (fp32): error ~2^-21, like FFMA.
 //
 // Persistent, warp-specialised (512 threads, 1 CTA/SM):
 //   warp 0      TMA producer   cp.async.bulk.tensor.2d (SWIZZLE_128B boxes of 32 fp32 = 128 B x rows)
@@ -115,7 +116,7 @@ struct Args {
   uint32_t* mask_out;  // EPI_BIAS_ACT + relu: bit j of word [m][n0/32] = (y[m][n0+j] > 0), for the backward
   const uint32_t* mask_in;  // EPI_ACT_GRAD + relu: the same words instead of re-reading the activations
   int64_t mask_ld;     // words per row
-  int32_t debug;       // HRB_TC_DEBUG bit mask (perf experiments only): 1 no stores, 2 no conversion, 4 no MMA, 8 no TMA
+  int32_t debug;       // HRB_TC_DEBUG bit mask (perf experiments only): 1 no stores, 2 no conversion, 4 no MMA, 8 no TMA, 16 also write hi back
 };
 
 template <int BN, int EPI>
@@ -246,7 +247,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
           h.y = __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u);
           h.z = __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u);
           h.w = __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u);
-          *p = h;
+          if (g.debug & 16) *p = h;  // the MMA reads only the TF32 bits of the raw fp32 operand: writing hi back is redundant
           reinterpret_cast<float4*>(st + A_BYTES)[i] = make_float4(x.x - h.x, x.y - h.y, x.z - h.z, x.w - h.w);
         }
         if (!(g.debug & 2))
@@ -258,7 +259,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
           h.y = __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u);
           h.z = __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u);
           h.w = __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u);
-          *p = h;
+          if (g.debug & 16) *p = h;  // the MMA reads only the TF32 bits of the raw fp32 operand: writing hi back is redundant
           reinterpret_cast<float4*>(st + 2 * A_BYTES + B_BYTES)[i] = make_float4(x.x - h.x, x.y - h.y, x.z - h.z, x.w - h.w);
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to UMMA

@@ -164,6 +164,7 @@ def main():
     ap.add_argument("--ids", default="uniform", choices=["uniform", "zipf"])
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-peer-lookup", action="store_true", help="N>1: forward through the all-to-all row exchange instead of NVLink peer loads")
     ap.add_argument("--scale-vocab", type=float, default=1.0, help="shrink every vocabulary (debug only; reported in config)")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -201,12 +202,13 @@ def main():
         # row-sharded tables: this rank holds rows r with r % world == rank (bit-identical to the rows of the full table)
         from handyrec_b200.sharded import ShardedDeepFMEngine, TorchDistComm, shard_rows
 
-        for f, v in enumerate(vocabs):
-            t = torch.empty(shard_rows(v, rank, world), EMB_DIM, device=dev)
+        comm = TorchDistComm()
+        tables, peer_ptrs = comm.alloc_tables(vocabs, EMB_DIM, dev)  # shards live in symmetric memory: peers map them over NVLink
+        for f, t in enumerate(tables):
             K.init_uniform(t, seed=7 + f, row_start=rank, row_step=world)
-            tables.append(t)
-        eng = ShardedDeepFMEngine(tables, vocabs, fields, N_DENSE, TorchDistComm(), dnn_hidden_units=DNN_HIDDEN, dnn_activation="relu",
-                                  batch_size=B, optimizer=args.optimizer, lr=1e-3, l2_embd=0.0, seed=2022)
+        eng = ShardedDeepFMEngine(tables, vocabs, fields, N_DENSE, comm, peer_ptrs=None if args.no_peer_lookup else peer_ptrs,
+                                  dnn_hidden_units=DNN_HIDDEN, dnn_activation="relu", batch_size=B, optimizer=args.optimizer, lr=1e-3,
+                                  l2_embd=0.0, seed=2022)
     NB = 4  # rotating pool of distinct batches (tables are 6.5 GB >> 126 MB L2: every step touches fresh rows)
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
     ids_pool, dense_pool, label_pool = [], [], []
@@ -285,7 +287,7 @@ def main():
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
     for s in range(reps):
-        if world == 1:
+        if world == 1 or eng.peer_lookup:
             eng.plan.forward(ids_pool[s % NB], out=eng.X0, fm=(eng.fm_w, eng.fm_w0), want_fm_sum=False)
         else:
             eng.exchange.forward(ids_pool[s % NB], eng.X0)
@@ -318,11 +320,13 @@ def main():
                 "traffic": None, "share_of_step": gemm_ms / total_phase, "flops_per_step": gemm_flops,
                 "peak_source": f"{peaks['source']} bf16 sustained (kernel timed inside a long step)",
                 "note": "fp32 parity needs 3 TF32 MMAs per product at half the bf16 rate: ceiling of this scheme = 1/6 = 0.167 of the bf16 peak (DESIGN.md 3); ncu tensor-pipe active 34-48% (profiles/r01_ncu_full_summary.md)"}
-    lk = "lookup_fm_fwd" if world == 1 else "sharded_lookup_fwd"
+    lk = "lookup_fm_fwd" if (world == 1 or eng.peer_lookup) else "sharded_lookup_fwd"
     lk_ach = lookup_bytes / (phases[lk] * 1e-3) / 1e9
-    rl_lookup = {"kernel": "hrb::lookup_tile_kernel (fused lookup + FM)" if world == 1 else "row exchange (route + all-to-all + gather + scatter)",
+    peer = world > 1 and eng.peer_lookup
+    rl_lookup = {"kernel": "hrb::lookup_tile_kernel (fused lookup + FM)" if world == 1 else
+                 ("hrb::lookup_tile_kernel reading row-sharded tables over NVLink peer mappings" if peer else "row exchange (route + all-to-all + gather + scatter)"),
                  "bound": "hbm", "achieved": lk_ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": lk_ach / peaks["hbm_gbs"],
-                 "traffic": 159.0e6 if world == 1 else None, "traffic_note": "dram read+write per launch from profiles/r01_ncu_full_summary.md",
+                 "traffic": 159.0e6 if world == 1 else None, "nvlink_bytes_per_step": None if world == 1 else B * len(vocabs) * EMB_DIM * 4 * (world - 1) / world, "traffic_note": "dram read+write per launch from profiles/r01_ncu_full_summary.md",
                  "peak_source": f"{peaks['source']} copy bandwidth", "bytes_per_sample": LOOKUP_BYTES_PER_SAMPLE, "in_step_ms": phases[lk],
                  "alone_ms": lookup_alone_ms, "alone_achieved": lookup_bytes / (lookup_alone_ms * 1e-3) / 1e9,
                  "alone_frac": lookup_bytes / (lookup_alone_ms * 1e-3) / 1e9 / peaks["hbm_gbs"]}
@@ -347,7 +351,7 @@ def main():
                    "global_batch": B * world, "tables_rows": sum(vocabs), "tables_gb": sum(vocabs) * EMB_DIM * 4 / 1e9, "ids": args.ids,
                    "optimizer": f"{args.optimizer} (dense params) + {eng.emb_opt} (touched embedding rows)", "l2_embd": 0.0,
                    "l2_flush": "inputs larger than L2 (6.5 GB of tables, rotating pool of 4 batches)", "scale_vocab": args.scale_vocab,
-                   "parallelism": "single GPU" if world == 1 else f"dp{world}: batch split, tables row-sharded (row % {world}), NCCL all-to-all for keys/rows/gradient rows, all-reduce for dense grads"},
+                   "parallelism": "single GPU" if world == 1 else f"dp{world}: batch split, tables row-sharded (row % {world}), forward = fused lookup+FM reading peer shards over NVLink (symmetric memory), backward = NCCL all-to-all of gradient rows to the owners, all-reduce for dense grads"},
         "e2e": {"value": B * world * args.steps / (e2e_ms * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": eng.h2d_bytes_per_step(B), "d2h_bytes_per_step": 4,
                 "ms_per_step": e2e_ms / args.steps, "last_loss": loss, "api": "DeepFMEngine.fit_batches (pinned host batches, prefetching copy stream, async loss read-back every step)",
                 "blocking_train_on_batch_samples_per_s": B * world * args.steps / (e2e_sync_ms * 1e-3)},

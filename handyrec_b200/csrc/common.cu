@@ -88,3 +88,20 @@ HRB_API int hrb_init_uniform(float* table, int64_t rows, int32_t dim, uint32_t s
   HRB_LAUNCH_CHECK();
   return HRB_OK;
 }
+
+// Let kernels launched on the current device dereference memory that lives on `peer_device` (NVLink / NVSwitch).
+HRB_API int hrb_enable_peer_access(int32_t peer_device) {
+  int cur = 0;
+  HRB_CUDA(cudaGetDevice(&cur));
+  if (cur == peer_device) return HRB_OK;
+  int can = 0;
+  HRB_CUDA(cudaDeviceCanAccessPeer(&can, cur, peer_device));
+  if (!can) return hrb::fail(HRB_UNSUPPORTED, "device %d cannot access device %d peer-to-peer", cur, peer_device);
+  cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+  if (e == cudaErrorPeerAccessAlreadyEnabled) {
+    cudaGetLastError();  // clear the sticky-less error state
+    return HRB_OK;
+  }
+  HRB_CUDA(e);
+  return HRB_OK;
+}

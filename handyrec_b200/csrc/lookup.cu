@@ -71,6 +71,10 @@ struct hrb_plan {
   uint32_t* d_hot_keys = nullptr;    // keys of every row of the tiny ("hot") tables (see bwd_hot_kernel)
   int32_t n_hot_keys = 0;
   std::vector<uint32_t> hot_lo, hot_len;
+  // row-sharded tables read over NVLink peer mappings (hrb_plan_set_peers): owner = id % n_ranks, local row = id / n_ranks
+  int32_t n_ranks = 1;
+  const float** d_peer_tab = nullptr;  // [n_ranks][n_tables] device pointers (peer-mapped for the other ranks)
+  int64_t* d_full_rows = nullptr;      // [n_tables] full vocabulary sizes
 };
 
 namespace hrb {
@@ -430,7 +434,8 @@ __global__ void __launch_bounds__(32 * G) lookup_tile_kernel(const FieldDev* __r
                                                             float* __restrict__ out, int64_t out_ld, int32_t pitch /* floats */,
                                                             const float* __restrict__ fm_w, const float* __restrict__ fm_w0,
                                                             float* __restrict__ fm_out, float* __restrict__ fm_sum,
-                                                            int32_t* __restrict__ oob) {
+                                                            int32_t* __restrict__ oob, const float* const* __restrict__ peer_tab,
+                                                            const int64_t* __restrict__ full_rows, int32_t n_ranks, int32_t n_tables) {
   constexpr int TS = 32;            // samples per tile
   constexpr int NT = 32 * G;        // threads: G lanes per sample
   constexpr int D = 4 * G;
@@ -466,8 +471,13 @@ __global__ void __launch_bounds__(32 * G) lookup_tile_kernel(const FieldDev* __r
         if (f0 + u < n_fields) {
           const FieldDev& f = fields[f0 + u];
           float* dst = my_row + (f0 + u) * D + q * 4;
-          if (valid && id[u] >= 0 && (int64_t)id[u] < f.rows) {
-            const float* src = f.table + (int64_t)id[u] * D + q * 4;
+          const int64_t vocab = peer_tab != nullptr ? __ldg(full_rows + f.table_idx) : f.rows;
+          if (valid && id[u] >= 0 && (int64_t)id[u] < vocab) {
+            const float* src;
+            if (peer_tab != nullptr)  // row-sharded table: the row lives on rank id % N (NVLink peer mapping) at local row id / N
+              src = peer_tab[(id[u] % n_ranks) * n_tables + f.table_idx] + (int64_t)(id[u] / n_ranks) * D + q * 4;
+            else
+              src = f.table + (int64_t)id[u] * D + q * 4;
             asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr_u32(dst)), "l"(src) : "memory");
           } else {
             *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -1177,6 +1187,8 @@ HRB_API int hrb_plan_create(const hrb_table_desc* tables_host, int32_t n_tables,
 HRB_API int hrb_plan_destroy(hrb_plan* plan) {
   if (plan == nullptr) return HRB_OK;
   if (plan->dev_blob) cudaFree(plan->dev_blob);
+  if (plan->d_peer_tab) cudaFree((void*)plan->d_peer_tab);
+  if (plan->d_full_rows) cudaFree(plan->d_full_rows);
   delete plan;
   return HRB_OK;
 }
@@ -1223,7 +1235,9 @@ static int launch_rows(const hrb_plan* plan, const int32_t* ids, int64_t ids_ld,
       attr = true;                                                                                                            \
     }                                                                                                                         \
     lookup_tile_kernel<GG, FM><<<(unsigned)grid, 32 * GG, smem, st>>>(plan->d_fields, plan->n_fields, ids, ids_ld, batch, out, \
-                                                                      out_ld, pitch, fm_w, fm_w0, fm_out, fm_sum, oob);       \
+                                                                      out_ld, pitch, fm_w, fm_w0, fm_out, fm_sum, oob,        \
+                                                                      plan->d_peer_tab, plan->d_full_rows, plan->n_ranks,     \
+                                                                      plan->n_tables);                                        \
   }
       switch (G) {
         case 2: HRB_TILE(2) break;
@@ -1236,6 +1250,8 @@ static int launch_rows(const hrb_plan* plan, const int32_t* ids, int64_t ids_ld,
       return HRB_OK;
     }
   }
+  if (plan->d_peer_tab != nullptr)
+    return fail(HRB_UNSUPPORTED, "peer-mapped (row-sharded) lookup is implemented for plain-lookup groups laid out contiguously only");
   const int spb = 256 / G;
   // enough CTAs for every SM to hold its full complement, persistent-style grid-stride over samples
   int64_t blocks = (batch + spb - 1) / spb;
@@ -1724,4 +1740,26 @@ HRB_API int hrb_keyed_bwd_update(const hrb_plan* plan, const uint32_t* keys, con
   if (opt_host->opt == HRB_OPT_ADAM_LAZY) ctx.lr_t = opt_host->lr * sqrtf(opt_host->bias_corr2) / opt_host->bias_corr1;
   return run_sorted_update(opt_host->opt == HRB_OPT_SGD ? 0 : 1, w, n, (uint32_t)plan->total_rows, plan->key_bits, plan->max_dim / 4, src, ctx,
                            hot_from_plan(plan), st);
+}
+
+// Row-sharded tables read in place over NVLink: `peer_tables_host[r*n_tables + t]` is the device pointer of rank r's shard
+// of table t as mapped into THIS process (own shards: the local pointers; other ranks: CUDA-IPC / symmetric-memory mappings);
+// `full_rows_host[t]` is the full vocabulary size.  Afterwards hrb_lookup_fwd / hrb_lookup_fm_fwd take GLOBAL ids and gather
+// row id from rank id % n_ranks at local row id / n_ranks -- no all-to-all in the forward pass.
+HRB_API int hrb_plan_set_peers(hrb_plan* plan, int32_t n_ranks, const void* const* peer_tables_host, const int64_t* full_rows_host) {
+  HRB_REQUIRE(plan && n_ranks >= 1 && peer_tables_host && full_rows_host, "hrb_plan_set_peers: bad argument");
+  if (!(plan->all_len1 && plan->uniform_dim && plan->contiguous_out))
+    return fail(HRB_UNSUPPORTED, "hrb_plan_set_peers: implemented for plain-lookup groups laid out contiguously only");
+  const size_t np = (size_t)n_ranks * plan->n_tables;
+  for (size_t i = 0; i < np; ++i) HRB_REQUIRE(peer_tables_host[i] != nullptr, "hrb_plan_set_peers: null table pointer");
+  if (plan->d_peer_tab) cudaFree((void*)plan->d_peer_tab);
+  if (plan->d_full_rows) cudaFree(plan->d_full_rows);
+  plan->d_peer_tab = nullptr;
+  plan->d_full_rows = nullptr;
+  HRB_CUDA(cudaMalloc((void**)&plan->d_peer_tab, np * sizeof(void*)));
+  HRB_CUDA(cudaMalloc((void**)&plan->d_full_rows, plan->n_tables * sizeof(int64_t)));
+  HRB_CUDA(cudaMemcpy((void*)plan->d_peer_tab, peer_tables_host, np * sizeof(void*), cudaMemcpyHostToDevice));
+  HRB_CUDA(cudaMemcpy(plan->d_full_rows, full_rows_host, plan->n_tables * sizeof(int64_t), cudaMemcpyHostToDevice));
+  plan->n_ranks = n_ranks;
+  return HRB_OK;
 }

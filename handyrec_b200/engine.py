@@ -278,6 +278,9 @@ class DeepFMEngine:
              K._p(self._ws_emb), self._ws_emb.numel(), st)
         self._mark("embedding_bwd_update")
 
+    def _pre_embedding_backward(self) -> None:
+        """Sharded engine: finish the routing exchange (host sync on data that is ready since the forward)."""
+
     def _sync_dense_grads(self) -> None:
         """Replicated dense parameters: the sharded engine all-reduces the flat gradient buffer here."""
 
@@ -332,6 +335,8 @@ class DeepFMEngine:
                 main = torch.cuda.current_stream()
                 if self._side is None:
                     self._side = torch.cuda.Stream()
+                with torch.cuda.stream(self._side):
+                    self._pre_embedding_backward()  # host-synchronising preparation that does not depend on the gradients
                 self._side.wait_stream(main)
                 with torch.cuda.stream(self._side):
                     self._embedding_backward(ids, B, K._stream(), op)

@@ -114,6 +114,27 @@ class TorchDistComm:
     def all_reduce_sum(self, t: torch.Tensor) -> None:
         self.dist.all_reduce(t, group=self.group)
 
+    def alloc_tables(self, vocabs: Sequence[int], dim: int, device) -> Tuple[List[torch.Tensor], Optional[List[List[int]]]]:
+        """Allocate this rank's shards in ONE symmetric-memory arena (torch.distributed._symmetric_memory: CUDA VMM
+        allocations exported to every rank of the node and mapped over NVLink) -> (tables, peer_ptrs[r][t]).
+        With the gloo backend (CPU tests) plain tensors are returned and peer_ptrs is None."""
+        rows = [shard_rows(v, self.rank, self.N) for v in vocabs]
+        if self.dist.get_backend(self.group) != "nccl":
+            return [torch.zeros(r, dim) for r in rows], None
+        import torch.distributed._symmetric_memory as symm_mem
+
+        max_rows = [shard_rows(v, 0, self.N) for v in vocabs]  # identical layout on every rank
+        offs, off = [], 0
+        for r in max_rows:
+            offs.append(off)
+            off += (r * dim + 63) // 64 * 64  # 256-byte aligned table starts
+        arena = symm_mem.empty((off,), dtype=torch.float32, device=device)
+        hdl = symm_mem.rendezvous(arena, group=self.group if self.group is not None else self.dist.group.WORLD)
+        self._arena, self._arena_hdl = arena, hdl  # keep the mapping alive
+        tables = [arena[o : o + r * dim].view(r, dim) for o, r in zip(offs, rows)]
+        peer_ptrs = [[int(hdl.buffer_ptrs[rk]) + o * 4 for o in offs] for rk in range(self.N)]
+        return tables, peer_ptrs
+
 
 class RowExchange:
     """The requester/owner protocol of one rank.  `provider` does the arithmetic, `comm` moves the bytes."""
@@ -122,19 +143,32 @@ class RowExchange:
         self.p, self.comm = provider, comm
         self.N = comm.N
 
-    def forward(self, ids: torch.Tensor, out: torch.Tensor) -> None:
-        perm, send_keys, counts = self.p.route(ids)
-        recv_counts_dev = self.comm.all_to_all_equal(counts[: self.N].contiguous())
-        both = torch.cat([counts[: self.N], recv_counts_dev]).tolist()  # the one host sync of the step
+    def route_async(self, ids: torch.Tensor) -> None:
+        """Launch the routing of `ids` (owner + key per position, grouped by owner) and the exchange of the per-rank counts;
+        nothing waits on the host.  Routing depends on the ids only, so it can run long before its results are needed."""
+        self.perm, self.send_keys, counts = self.p.route(ids)
+        self._counts_dev = counts
+        self._recv_counts_dev = self.comm.all_to_all_equal(counts[: self.N].contiguous())
+        self._routed = False
+
+    def finish_route(self) -> None:
+        if self._routed:
+            return
+        both = torch.cat([self._counts_dev[: self.N], self._recv_counts_dev]).tolist()  # the one host sync of the step
         self.send_counts, self.recv_counts = [int(x) for x in both[: self.N]], [int(x) for x in both[self.N :]]
         self.n_send, self.n_recv = sum(self.send_counts), sum(self.recv_counts)
-        self.perm = perm
-        self.recv_keys = self.comm.all_to_all_v(send_keys[: self.n_send], self.send_counts, self.recv_counts)
+        self.recv_keys = self.comm.all_to_all_v(self.send_keys[: self.n_send], self.send_counts, self.recv_counts)
+        self._routed = True
+
+    def forward(self, ids: torch.Tensor, out: torch.Tensor) -> None:
+        self.route_async(ids)
+        self.finish_route()
         rows = self.p.rows_by_key(self.recv_keys, self.n_recv)
         got = self.comm.all_to_all_v(rows, self.recv_counts, self.send_counts)
-        self.p.scatter_rows(ids, perm, self.n_send, got, out)
+        self.p.scatter_rows(ids, self.perm, self.n_send, got, out)
 
     def backward_update(self, ids: torch.Tensor, dout: torch.Tensor, op) -> None:
+        self.finish_route()
         send = self.p.gather_grads(ids, self.perm, self.n_send, dout)
         recv = self.comm.all_to_all_v(send, self.send_counts, self.recv_counts)
         self.p.keyed_update(self.recv_keys, recv, self.n_recv, op)
@@ -147,7 +181,7 @@ class ShardedDeepFMEngine(DeepFMEngine):
     The per-rank batch is fixed (weak scaling); gradients are averaged over the global batch.
     """
 
-    def __init__(self, tables, vocabs, fields, n_dense, comm, **kw):
+    def __init__(self, tables, vocabs, fields, n_dense, comm, peer_ptrs=None, **kw):
         super().__init__(tables, fields, n_dense, **kw)
         self.comm = comm
         self.world = comm.N
@@ -155,16 +189,47 @@ class ShardedDeepFMEngine(DeepFMEngine):
         self.exchange = RowExchange(self.provider, comm)
         self.grad_scale_div = comm.N
         self.overlap_embedding_bwd = True
+        self.peer_lookup = False
+        self._emb_pending = None
+        self._barrier_buf = torch.zeros(1, device=self.dev)
+        if peer_ptrs is not None and all(f[1] == 1 and f[2] in ("none", None) for f in fields):
+            # forward without any all-to-all: every rank maps every other rank's shards (comm.alloc_tables: symmetric memory over
+            # NVLink) and the fused lookup+FM kernel gathers row `id` from rank id % N at local row id // N
+            n_t = len(self.tables)
+            ptrs = (ctypes.c_void_p * (comm.N * n_t))(*[int(peer_ptrs[r][t]) for r in range(comm.N) for t in range(n_t)])
+            full = (ctypes.c_int64 * n_t)(*[int(v) for v in vocabs])
+            call("hrb_plan_set_peers", self.plan._h, comm.N, ptrs, full)
+            self.peer_lookup = True
 
     def _lookup_fm_forward(self, ids, B, st):
-        emb = self.X0[:, self.nd_pad :]
+        if self.peer_lookup:
+            # the routing needed by the BACKWARD exchange depends on the ids only: launch it now, beside the forward
+            main = torch.cuda.current_stream()
+            if self._side is None:
+                self._side = torch.cuda.Stream()
+            if self._marks is None:
+                self._side.wait_stream(main)
+                with torch.cuda.stream(self._side):
+                    self.exchange.route_async(ids)
+            else:
+                self.exchange.route_async(ids)
+            super()._lookup_fm_forward(ids, B, st)
+            return
         self.exchange.forward(ids, self.X0)  # the plan's out_col already includes the dense block
         self._mark("sharded_lookup_fwd")
+        emb = self.X0[:, self.nd_pad :]
         call("hrb_fm_fwd", K._p(emb), self.K0p, B, self.F, self.D, K._p(self.fm_w), K._p(self.fm_w0), K._p(self.fm_out), K._p(self.fm_sum), st)
         self._mark("fm_fwd")
 
+    def _pre_embedding_backward(self):
+        if self.peer_lookup:
+            self.exchange.finish_route()
+
     def _embedding_backward(self, ids, B, st, op):
         self.exchange.backward_update(ids, self.dX0, op)
+        if self.peer_lookup:
+            # peers read this shard in the next forward: nobody may start it before every rank has finished updating
+            self.comm.all_reduce_sum(self._barrier_buf)
         self._mark("sharded_embedding_bwd_update")
 
     def _sync_dense_grads(self):

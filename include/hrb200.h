@@ -301,6 +301,12 @@ int hrb_lookup_combine(const hrb_plan* plan, const float* psum, const float* pco
  *   requester  hrb_scatter_rows  rows -> output block (plain features) / position buffer + pooling (sequence features)
  *   requester  hrb_gather_grads  send[j,:] = dout[b, field(perm[j]) columns] * (1/n_valid for mean pooling)
  *   owner      hrb_keyed_bwd_update  (key, gradient row) pairs -> sort -> segment-reduce -> SGD / lazy-Adam row update */
+/* Peer-mapped lookup: peer_tables_host[r*n_tables + t] = device pointer of rank r's shard of table t as mapped into this
+ * process (CUDA IPC / symmetric memory over NVLink), full_rows_host[t] = full vocabulary size.  After this call
+ * hrb_lookup_fwd / hrb_lookup_fm_fwd take GLOBAL ids and read row id from rank id % n_ranks at local row id / n_ranks:
+ * the forward needs no all-to-all (plain-lookup groups laid out contiguously only). */
+int hrb_enable_peer_access(int32_t peer_device); /* cudaDeviceEnablePeerAccess from the current device, idempotent */
+int hrb_plan_set_peers(hrb_plan* plan, int32_t n_ranks, const void* const* peer_tables_host, const int64_t* full_rows_host);
 int hrb_route_workspace(const hrb_plan* plan, int64_t batch, size_t* bytes);
 int hrb_route_ids(const hrb_plan* plan, const int32_t* ids, int64_t ids_ld, int64_t batch, int32_t n_ranks,
                   const uint32_t* key_base, uint32_t* perm, uint32_t* send_keys, int64_t* counts, void* workspace,

@@ -157,12 +157,13 @@ class ThreadComm:
         self.s, self.rank, self.N = shared, rank, shared.n
 
     def _exchange(self, pieces):
-        if pieces[0].is_cuda:  # emulated ranks share one GPU but use different streams: publish only finished data
+        if isinstance(pieces[0], torch.Tensor) and pieces[0].is_cuda:  # emulated ranks share one GPU but use different streams: publish only finished data
             torch.cuda.current_stream().synchronize()
         for dst, t in enumerate(pieces):
             self.s.slots[self.rank][dst] = t
         self.s.barrier.wait()
-        got = [self.s.slots[src][self.rank].clone() for src in range(self.N)]
+        got = [self.s.slots[src][self.rank] for src in range(self.N)]
+        got = [g.clone() if isinstance(g, torch.Tensor) else g for g in got]
         self.s.barrier.wait()
         return got
 
@@ -177,3 +178,8 @@ class ThreadComm:
     def all_reduce_sum(self, t):
         got = self._exchange([t.clone() for _ in range(self.N)])
         t.copy_(torch.stack(got).sum(0))
+
+    def share_ptrs(self, tables):
+        # one process, one GPU: the "peer mappings" are the other threads' tensors themselves
+        got = self._exchange([[int(t.data_ptr()) for t in tables] for _ in range(self.N)])
+        return got

@@ -68,8 +68,8 @@ def test_row_exchange_cuda(dev, world, opt):
                 close(s[: ws.shape[0]], ws, 1e-4)
 
 
-@pytest.mark.parametrize("world,b", [(2, 64), (4, 64), (2, 512)])
-def test_sharded_engine_matches_single_gpu_engine(dev, world, b):
+@pytest.mark.parametrize("world,b,peer", [(2, 64, True), (4, 64, False), (2, 512, True), (2, 512, False), (8, 64, True)])
+def test_sharded_engine_matches_single_gpu_engine(dev, world, b, peer):
     """N emulated ranks with row-sharded tables take the same SGD step as one engine on the concatenated batch."""
     from handyrec_b200 import kernels as K
     from handyrec_b200.engine import DeepFMEngine
@@ -91,8 +91,11 @@ def test_sharded_engine_matches_single_gpu_engine(dev, world, b):
 
     def rank_fn(r):
         sh = [t.to(dev) for t in H.shards_of(tables, r, world)]
-        eng = ShardedDeepFMEngine(sh, vocabs, fields, n_dense, H.ThreadComm(shared, r), dnn_hidden_units=hidden, dnn_activation="relu",
+        comm = H.ThreadComm(shared, r)
+        peer_ptrs = comm.share_ptrs(sh) if peer else None  # peer-mapped forward (no all-to-all) vs. row-exchange forward
+        eng = ShardedDeepFMEngine(sh, vocabs, fields, n_dense, comm, peer_ptrs=peer_ptrs, dnn_hidden_units=hidden, dnn_activation="relu",
                                   batch_size=b, optimizer="sgd", lr=0.1, seed=7)
+        assert eng.peer_lookup == peer
         engines[r] = eng
         eng.train_step_on_device(ids[r].to(dev), dense[r].to(dev), label[r].to(dev))
         torch.cuda.synchronize()

@@ -165,6 +165,8 @@ def main():
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-peer-lookup", action="store_true", help="N>1: forward through the all-to-all row exchange instead of NVLink peer loads")
+    ap.add_argument("--small-table-rows", type=int, default=131072,
+                    help="tables up to this many rows take the dense (Keras-exact) optimiser step; at N>1 they are replicated instead of sharded (0 = off)")
     ap.add_argument("--scale-vocab", type=float, default=1.0, help="shrink every vocabulary (debug only; reported in config)")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -197,18 +199,23 @@ def main():
             t = torch.empty(v, EMB_DIM, device=dev)
             K.init_uniform(t, seed=7 + f)
             tables.append(t)
-        eng = DeepFMEngine(tables, fields, N_DENSE, DNN_HIDDEN, "relu", batch_size=B, optimizer=args.optimizer, lr=1e-3, l2_embd=0.0, seed=2022)
+        eng = DeepFMEngine(tables, fields, N_DENSE, DNN_HIDDEN, "relu", batch_size=B, optimizer=args.optimizer, lr=1e-3, l2_embd=0.0, seed=2022,
+                           dense_table_max_rows=args.small_table_rows)
     else:
         # row-sharded tables: this rank holds rows r with r % world == rank (bit-identical to the rows of the full table)
         from handyrec_b200.sharded import ShardedDeepFMEngine, TorchDistComm, shard_rows
 
         comm = TorchDistComm()
-        tables, peer_ptrs = comm.alloc_tables(vocabs, EMB_DIM, dev)  # shards live in symmetric memory: peers map them over NVLink
+        # shards live in symmetric memory (peers map them over NVLink); small tables are replicated in full on every rank
+        tables, peer_ptrs = comm.alloc_tables(vocabs, EMB_DIM, dev, replicate_max_rows=args.small_table_rows)
         for f, t in enumerate(tables):
-            K.init_uniform(t, seed=7 + f, row_start=rank, row_step=world)
+            if vocabs[f] <= args.small_table_rows:
+                K.init_uniform(t, seed=7 + f)
+            else:
+                K.init_uniform(t, seed=7 + f, row_start=rank, row_step=world)
         eng = ShardedDeepFMEngine(tables, vocabs, fields, N_DENSE, comm, peer_ptrs=None if args.no_peer_lookup else peer_ptrs,
                                   dnn_hidden_units=DNN_HIDDEN, dnn_activation="relu", batch_size=B, optimizer=args.optimizer, lr=1e-3,
-                                  l2_embd=0.0, seed=2022)
+                                  l2_embd=0.0, seed=2022, replicate_max_rows=args.small_table_rows)
     NB = 4  # rotating pool of distinct batches (tables are 6.5 GB >> 126 MB L2: every step touches fresh rows)
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
     ids_pool, dense_pool, label_pool = [], [], []
@@ -323,10 +330,12 @@ def main():
     lk = "lookup_fm_fwd" if (world == 1 or eng.peer_lookup) else "sharded_lookup_fwd"
     lk_ach = lookup_bytes / (phases[lk] * 1e-3) / 1e9
     peer = world > 1 and eng.peer_lookup
+    n_small = sum(1 for v in vocabs if v <= args.small_table_rows)
+    n_sharded = len(vocabs) - n_small
     rl_lookup = {"kernel": "hrb::lookup_tile_kernel (fused lookup + FM)" if world == 1 else
                  ("hrb::lookup_tile_kernel reading row-sharded tables over NVLink peer mappings" if peer else "row exchange (route + all-to-all + gather + scatter)"),
                  "bound": "hbm", "achieved": lk_ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": lk_ach / peaks["hbm_gbs"],
-                 "traffic": 159.0e6 if world == 1 else None, "nvlink_bytes_per_step": None if world == 1 else B * len(vocabs) * EMB_DIM * 4 * (world - 1) / world, "traffic_note": "dram read+write per launch from profiles/r01_ncu_full_summary.md",
+                 "traffic": 159.0e6 if world == 1 else None, "nvlink_bytes_per_step": None if world == 1 else B * n_sharded * EMB_DIM * 4 * (world - 1) / world, "traffic_note": "dram read+write per launch from profiles/r01_ncu_full_summary.md",
                  "peak_source": f"{peaks['source']} copy bandwidth", "bytes_per_sample": LOOKUP_BYTES_PER_SAMPLE, "in_step_ms": phases[lk],
                  "alone_ms": lookup_alone_ms, "alone_achieved": lookup_bytes / (lookup_alone_ms * 1e-3) / 1e9,
                  "alone_frac": lookup_bytes / (lookup_alone_ms * 1e-3) / 1e9 / peaks["hbm_gbs"]}
@@ -334,9 +343,10 @@ def main():
     uniq = int(sum(torch.unique(ids_pool[0][:, f]).numel() for f in range(len(vocabs))))
     S = 3 if eng.emb_opt == "adam_lazy" else 1
     eb_bytes = B * len(vocabs) * (4 + EMB_DIM * 4) + uniq * EMB_DIM * 4 * 2 * S
-    eb_ach = eb_bytes / (phases[eb] * 1e-3) / 1e9
+    eb_ms = phases.get(eb, 0.0) + phases.get("replicated_embedding_bwd", 0.0)
+    eb_ach = eb_bytes / (eb_ms * 1e-3) / 1e9
     rl_emb = {"kernel": "bwd_keys + radix sort + bwd_chunk/hot/merge (a13)", "bound": "hbm", "achieved": eb_ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-              "frac": eb_ach / peaks["hbm_gbs"], "unique_rows": uniq, "bytes_per_step": eb_bytes, "in_step_ms": phases[eb]}
+              "frac": eb_ach / peaks["hbm_gbs"], "unique_rows": uniq, "bytes_per_step": eb_bytes, "in_step_ms": eb_ms}
 
     cpu = None
     if not args.no_cpu_baseline:
@@ -349,9 +359,9 @@ def main():
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": "DeepFM Criteo-shape: 26 sparse + 13 dense, emb dim 16, DNN 429-256-128-1, batch 65536/GPU (BASELINE.json configs[2])",
                    "global_batch": B * world, "tables_rows": sum(vocabs), "tables_gb": sum(vocabs) * EMB_DIM * 4 / 1e9, "ids": args.ids,
-                   "optimizer": f"{args.optimizer} (dense params) + {eng.emb_opt} (touched embedding rows)", "l2_embd": 0.0,
+                   "optimizer": f"{args.optimizer} (dense params and the {n_small} tables of <= {args.small_table_rows} rows, Keras-exact dense step) + {eng.emb_opt} (touched rows of the {n_sharded} large tables)", "l2_embd": 0.0,
                    "l2_flush": "inputs larger than L2 (6.5 GB of tables, rotating pool of 4 batches)", "scale_vocab": args.scale_vocab,
-                   "parallelism": "single GPU" if world == 1 else f"dp{world}: batch split, tables row-sharded (row % {world}), forward = fused lookup+FM reading peer shards over NVLink (symmetric memory), backward = NCCL all-to-all of gradient rows to the owners, all-reduce for dense grads"},
+                   "parallelism": "single GPU" if world == 1 else f"dp{world}: batch split, {n_sharded} large tables row-sharded (row % {world}), {n_small} small tables replicated (gradients all-reduced with the dense ones), forward = fused lookup+FM reading peer shards over NVLink (symmetric memory), backward = NCCL all-to-all of gradient rows to the owners, all-reduce for dense grads"},
         "e2e": {"value": B * world * args.steps / (e2e_ms * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": eng.h2d_bytes_per_step(B), "d2h_bytes_per_step": 4,
                 "ms_per_step": e2e_ms / args.steps, "last_loss": loss, "api": "DeepFMEngine.fit_batches (pinned host batches, prefetching copy stream, async loss read-back every step)",
                 "blocking_train_on_batch_samples_per_s": B * world * args.steps / (e2e_sync_ms * 1e-3)},

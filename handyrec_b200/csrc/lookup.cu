@@ -42,6 +42,7 @@ struct TableDev {
   int64_t rows;
   uint32_t key_base;
   int32_t dim;
+  float* grad;  // non-null: a13 adds the row's gradient sum here instead of updating the row (hrb_plan_set_dense_grads)
 };
 
 }  // namespace hrb
@@ -435,16 +436,23 @@ __global__ void __launch_bounds__(32 * G) lookup_tile_kernel(const FieldDev* __r
                                                             const float* __restrict__ fm_w, const float* __restrict__ fm_w0,
                                                             float* __restrict__ fm_out, float* __restrict__ fm_sum,
                                                             int32_t* __restrict__ oob, const float* const* __restrict__ peer_tab,
-                                                            const int64_t* __restrict__ full_rows, int32_t n_ranks, int32_t n_tables) {
+                                                            const int64_t* __restrict__ full_rows, int32_t n_ranks, int32_t n_tables,
+                                                            int32_t gmode) {
   constexpr int TS = 32;            // samples per tile
   constexpr int NT = 32 * G;        // threads: G lanes per sample
   constexpr int D = 4 * G;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float* tile = reinterpret_cast<float*>(smem_raw);                                   // [TS][pitch]
   FieldDev* fields = reinterpret_cast<FieldDev*>(smem_raw + (size_t)TS * pitch * 4);  // descriptors
+  __shared__ __align__(8) uint64_t gbar;
   for (int i = threadIdx.x; i < n_fields * (int)(sizeof(FieldDev) / 4); i += NT)
     reinterpret_cast<uint32_t*>(fields)[i] = reinterpret_cast<const uint32_t*>(fields_g)[i];
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr_u32(&gbar)), "r"(NT));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
   __syncthreads();
+  uint32_t gphase = 0;
   const int q = threadIdx.x % G, s = threadIdx.x / G;
   float4 w4 = make_float4(0.f, 0.f, 0.f, 0.f);
   float w0 = 0.f;
@@ -462,8 +470,44 @@ __global__ void __launch_bounds__(32 * G) lookup_tile_kernel(const FieldDev* __r
     float* my_row = tile + (size_t)s * pitch;
     // gather: ids first (independent loads), then one 16-byte async copy per (field, chunk)
     constexpr int FU = 13;
+    if (gmode == 1) {
+      // experiment: one 1-D bulk copy (TMA) per row, lane q takes fields f == q (mod G)
+      uint32_t tx = 0;
+      for (int f = q; f < n_fields; f += G) {
+        const FieldDev& fd = fields[f];
+        const int32_t id = valid ? __ldg(ids_row + fd.ids_col) : -1;
+        float* dst = my_row + f * D;
+        const bool remote = peer_tab != nullptr && peer_tab[fd.table_idx] != nullptr;
+        const int64_t vocab = remote ? __ldg(full_rows + fd.table_idx) : fd.rows;
+        if (valid && id >= 0 && (int64_t)id < vocab) {
+          const float* src = remote ? peer_tab[(id % n_ranks) * n_tables + fd.table_idx] + (int64_t)(id / n_ranks) * D
+                                    : fd.table + (int64_t)id * D;
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr_u32(dst)),
+                       "l"(src), "r"((uint32_t)(D * 4)), "r"(smem_addr_u32(&gbar))
+                       : "memory");
+          tx += D * 4;
+        } else {
+#pragma unroll
+          for (int k = 0; k < G; ++k) reinterpret_cast<float4*>(dst)[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (valid && oob != nullptr) {
+            oob[0] = 1;
+            oob[1] = (int32_t)b;
+          }
+        }
+      }
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr_u32(&gbar)), "r"(tx) : "memory");
+      uint32_t done = 0;
+      while (!done)
+        asm volatile(
+            "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+            : "=r"(done)
+            : "r"(smem_addr_u32(&gbar)), "r"(gphase)
+            : "memory");
+      gphase ^= 1;
+    } else {
     for (int f0 = 0; f0 < n_fields; f0 += FU) {
       int32_t id[FU];
+      float4 val[FU];
 #pragma unroll
       for (int u = 0; u < FU; ++u) id[u] = (valid && f0 + u < n_fields) ? __ldg(ids_row + fields[f0 + u].ids_col) : 0;
 #pragma unroll
@@ -471,16 +515,22 @@ __global__ void __launch_bounds__(32 * G) lookup_tile_kernel(const FieldDev* __r
         if (f0 + u < n_fields) {
           const FieldDev& f = fields[f0 + u];
           float* dst = my_row + (f0 + u) * D + q * 4;
-          const int64_t vocab = peer_tab != nullptr ? __ldg(full_rows + f.table_idx) : f.rows;
+          // a table without peer pointers is replicated: read the local copy
+          const bool remote = peer_tab != nullptr && peer_tab[f.table_idx] != nullptr;
+          const int64_t vocab = remote ? __ldg(full_rows + f.table_idx) : f.rows;
           if (valid && id[u] >= 0 && (int64_t)id[u] < vocab) {
             const float* src;
-            if (peer_tab != nullptr)  // row-sharded table: the row lives on rank id % N (NVLink peer mapping) at local row id / N
+            if (remote)  // row-sharded table: the row lives on rank id % N (NVLink peer mapping) at local row id / N
               src = peer_tab[(id[u] % n_ranks) * n_tables + f.table_idx] + (int64_t)(id[u] / n_ranks) * D + q * 4;
             else
               src = f.table + (int64_t)id[u] * D + q * 4;
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr_u32(dst)), "l"(src) : "memory");
+            if (gmode == 2)
+              val[u] = ldg_nc_na(reinterpret_cast<const float4*>(src));
+            else
+              asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr_u32(dst)), "l"(src) : "memory");
           } else {
-            *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+            val[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (gmode != 2) *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
             if (valid && oob != nullptr) {
               oob[0] = 1;
               oob[1] = (int32_t)b;
@@ -488,9 +538,15 @@ __global__ void __launch_bounds__(32 * G) lookup_tile_kernel(const FieldDev* __r
           }
         }
       }
+      if (gmode == 2) {
+#pragma unroll
+        for (int u = 0; u < FU; ++u)
+          if (f0 + u < n_fields) *reinterpret_cast<float4*>(my_row + (f0 + u) * D + q * 4) = val[u];
+      }
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
     asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // rows must be visible to the bulk-store engine
     __syncthreads();
     // one bulk store per sample row (1664 B at F=26, D=16): shared -> global, full lines
@@ -691,6 +747,13 @@ __device__ __forceinline__ void apply_row(const ApplyCtx& c, uint32_t key, int q
   const TableDev& t = c.tables[ti];
   if (q * 4 >= t.dim) return;
   const int64_t off = (int64_t)(key - t.key_base) * (t.dim >> 2) + q;
+  if (t.grad != nullptr) {  // dense-updated table: hand the gradient sum to the caller's dense optimiser step
+    float4* gp = reinterpret_cast<float4*>(t.grad) + off;
+    float4 o = *gp;
+    o.x += g.x; o.y += g.y; o.z += g.z; o.w += g.w;
+    *gp = o;
+    return;
+  }
   float4* wp = reinterpret_cast<float4*>(t.w) + off;
   float4 w = *wp;
   const float l2 = c.opt.l2_scale;
@@ -1106,7 +1169,7 @@ HRB_API int hrb_plan_create(const hrb_table_desc* tables_host, int32_t n_tables,
       return fail(td.dim % 4 ? HRB_UNSUPPORTED : HRB_BAD_ARG,
                   "hrb_plan_create: table %d needs a 16-byte aligned weight, rows>0 and dim%%4==0 (dim=%d)", t, td.dim);
     }
-    p->tdev_host[t] = TableDev{td.weight, td.adam_m, td.adam_v, td.rows, (uint32_t)base, td.dim};
+    p->tdev_host[t] = TableDev{td.weight, td.adam_m, td.adam_v, td.rows, (uint32_t)base, td.dim, nullptr};
     base += (uint64_t)td.rows;
     if (td.dim > p->max_dim) p->max_dim = td.dim;
   }
@@ -1227,6 +1290,11 @@ static int launch_rows(const hrb_plan* plan, const int32_t* ids, int64_t ids_ld,
       int64_t tiles = (batch + 31) / 32;
       int64_t grid = (int64_t)sm_count() * (per_sm < 1 ? 1 : (per_sm > 8 ? 8 : per_sm));
       if (grid > tiles) grid = tiles;
+      static int gmode = -1;
+      if (gmode < 0) {
+        const char* e = getenv("HRB_LOOKUP_GATHER");
+        gmode = e == nullptr ? 0 : (strcmp(e, "bulk") == 0 ? 1 : (strcmp(e, "ldg") == 0 ? 2 : 0));
+      }
 #define HRB_TILE(GG)                                                                                                          \
   {                                                                                                                           \
     static bool attr = false;                                                                                                 \
@@ -1237,7 +1305,7 @@ static int launch_rows(const hrb_plan* plan, const int32_t* ids, int64_t ids_ld,
     lookup_tile_kernel<GG, FM><<<(unsigned)grid, 32 * GG, smem, st>>>(plan->d_fields, plan->n_fields, ids, ids_ld, batch, out, \
                                                                       out_ld, pitch, fm_w, fm_w0, fm_out, fm_sum, oob,        \
                                                                       plan->d_peer_tab, plan->d_full_rows, plan->n_ranks,     \
-                                                                      plan->n_tables);                                        \
+                                                                      plan->n_tables, gmode);                                 \
   }
       switch (G) {
         case 2: HRB_TILE(2) break;
@@ -1338,7 +1406,7 @@ HRB_API int hrb_lookup_bwd_update(const hrb_plan* plan, const int32_t* ids, int6
   HRB_REQUIRE(opt_host->opt == HRB_OPT_SGD || opt_host->opt == HRB_OPT_ADAM_LAZY, "hrb_lookup_bwd_update: unknown optimiser %d", opt_host->opt);
   if (opt_host->opt == HRB_OPT_ADAM_LAZY)
     for (const auto& t : plan->tdev_host)
-      HRB_REQUIRE(t.m && t.v, "hrb_lookup_bwd_update: lazy Adam needs adam_m/adam_v for every table");
+      HRB_REQUIRE(t.grad || (t.m && t.v), "hrb_lookup_bwd_update: lazy Adam needs adam_m/adam_v for every table");
   const int G = plan->max_dim / 4;
   if (G > 256) return fail(HRB_UNSUPPORTED, "hrb_lookup_bwd_update: dim %d too large", plan->max_dim);
   if (batch == 0) return HRB_OK;
@@ -1746,12 +1814,25 @@ HRB_API int hrb_keyed_bwd_update(const hrb_plan* plan, const uint32_t* keys, con
 // of table t as mapped into THIS process (own shards: the local pointers; other ranks: CUDA-IPC / symmetric-memory mappings);
 // `full_rows_host[t]` is the full vocabulary size.  Afterwards hrb_lookup_fwd / hrb_lookup_fm_fwd take GLOBAL ids and gather
 // row id from rank id % n_ranks at local row id / n_ranks -- no all-to-all in the forward pass.
+HRB_API int hrb_plan_set_dense_grads(hrb_plan* plan, float* const* grads_host) {
+  HRB_REQUIRE(plan && grads_host, "hrb_plan_set_dense_grads: bad argument");
+  for (int32_t t = 0; t < plan->n_tables; ++t) {
+    HRB_REQUIRE(aligned16(grads_host[t]), "hrb_plan_set_dense_grads: gradient buffer of table %d is not 16-byte aligned", t);
+    plan->tdev_host[t].grad = grads_host[t];
+  }
+  HRB_CUDA(cudaMemcpy(plan->d_tables, plan->tdev_host.data(), sizeof(hrb::TableDev) * plan->n_tables, cudaMemcpyHostToDevice));
+  return HRB_OK;
+}
+
 HRB_API int hrb_plan_set_peers(hrb_plan* plan, int32_t n_ranks, const void* const* peer_tables_host, const int64_t* full_rows_host) {
   HRB_REQUIRE(plan && n_ranks >= 1 && peer_tables_host && full_rows_host, "hrb_plan_set_peers: bad argument");
   if (!(plan->all_len1 && plan->uniform_dim && plan->contiguous_out))
     return fail(HRB_UNSUPPORTED, "hrb_plan_set_peers: implemented for plain-lookup groups laid out contiguously only");
   const size_t np = (size_t)n_ranks * plan->n_tables;
-  for (size_t i = 0; i < np; ++i) HRB_REQUIRE(peer_tables_host[i] != nullptr, "hrb_plan_set_peers: null table pointer");
+  for (int32_t t = 0; t < plan->n_tables; ++t)  // a table is sharded (pointers on every rank) or replicated (NULL on every rank)
+    for (int32_t r = 1; r < n_ranks; ++r)
+      HRB_REQUIRE((peer_tables_host[(size_t)r * plan->n_tables + t] == nullptr) == (peer_tables_host[t] == nullptr),
+                  "hrb_plan_set_peers: table %d has peer pointers on some ranks only", t);
   if (plan->d_peer_tab) cudaFree((void*)plan->d_peer_tab);
   if (plan->d_full_rows) cudaFree(plan->d_full_rows);
   plan->d_peer_tab = nullptr;

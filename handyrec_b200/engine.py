@@ -45,6 +45,12 @@ class DeepFMEngine:
 
     fields: list of (table_index, seq_len, pool) in reference order (sparse features first, then
     sequence features, features/group.py:319-334); all tables must share one embedding dim.
+
+    Embedding optimiser.  Tables listed in `dense_update_tables` (default: every table with at most
+    `dense_table_max_rows` rows) are "dense-updated": the engine re-homes them at the end of its flat parameter
+    buffer (`engine.tables[t]` is the live table), their row gradients are reduced into the flat gradient buffer and
+    they take the same optimiser step as the dense parameters -- exactly Keras' treatment of an IndexedSlices
+    gradient (dense moment decay and dense l2_embd).  Every other table gets the touched-rows-only update.
     """
 
     def __init__(
@@ -63,6 +69,8 @@ class DeepFMEngine:
         seed: int = 2022,
         gemm_mode: int = _lib.GEMM_AUTO,
         task: str = "binary",
+        dense_table_max_rows: int = 0,
+        dense_update_tables: Optional[Sequence[int]] = None,
     ):
         if dnn_hidden_units[-1] != 1:  # DeepFM.py:59-60
             raise ValueError("Output size of dnn should be 1")
@@ -93,11 +101,10 @@ class DeepFMEngine:
             plan_fields.append((ti, L, pool if (L > 1 or pool not in (None, "none")) else "none", col, self.nd_pad + f * self.D))
             col += L
         self.ids_cols = col
-        self.adam_m = self.adam_v = None
-        if self.emb_opt == "adam_lazy":
-            self.adam_m = [torch.zeros_like(t) for t in self.tables]
-            self.adam_v = [torch.zeros_like(t) for t in self.tables]
-        self.plan = K.LookupPlan(self.tables, plan_fields, self.adam_m, self.adam_v)
+        self.plan_fields = plan_fields
+        if dense_update_tables is None:
+            dense_update_tables = [t for t, w in enumerate(self.tables) if w.shape[0] <= dense_table_max_rows]
+        self.dense_tables = sorted(set(int(t) for t in dense_update_tables))
 
         # ---- dense parameters: one flat buffer ----
         self.K0 = self.n_dense + self.F * self.D           # logical DNN input width
@@ -119,6 +126,11 @@ class DeepFMEngine:
         self.fm_off = off
         off += _r4(self.D + 1)
         self._segments.append((self.fm_off, off - self.fm_off, False))
+        self.n_dense_params = off
+        self._table_off = {}
+        for t in self.dense_tables:  # dense-updated tables live behind the dense parameters
+            self._table_off[t] = off
+            off += self.tables[t].numel()
         self.n_params = off
         self.params = torch.zeros(off, device=self.dev, dtype=torch.float32)
         self.grads = torch.zeros(off, device=self.dev, dtype=torch.float32)
@@ -134,6 +146,21 @@ class DeepFMEngine:
         self.fm_w0 = self.params[self.fm_off + self.D : self.fm_off + self.D + 1]
         self.d_fm = self.grads[self.fm_off : self.fm_off + self.D + 1]
         self._init_dense(seed)
+        table_grads: List[Optional[torch.Tensor]] = [None] * len(self.tables)
+        for t, o in self._table_off.items():
+            n = self.tables[t].numel()
+            live = self.params[o : o + n].view_as(self.tables[t])
+            live.copy_(self.tables[t])
+            self.tables[t] = live
+            table_grads[t] = self.grads[o : o + n].view_as(live)
+        self.table_grads = table_grads
+        self.adam_m = self.adam_v = None
+        if self.emb_opt == "adam_lazy":
+            self.adam_m = [None if t in self._table_off else torch.zeros_like(w) for t, w in enumerate(self.tables)]
+            self.adam_v = [None if t in self._table_off else torch.zeros_like(w) for t, w in enumerate(self.tables)]
+        self.plan = K.LookupPlan(self.tables, plan_fields, self.adam_m, self.adam_v)
+        if self.dense_tables:
+            self.plan.set_dense_grads(table_grads)
 
         # ---- batch buffers ----
         B = self.B
@@ -273,7 +300,12 @@ class DeepFMEngine:
              K._p(self.fm_w0), K._p(self.fm_out), K._p(self.fm_sum), None, st)
         self._mark("lookup_fm_fwd")
 
+    def _zero_table_grads(self) -> None:
+        if self.n_params > self.n_dense_params:
+            self.grads[self.n_dense_params :].zero_()
+
     def _embedding_backward(self, ids, B, st, op) -> None:
+        self._zero_table_grads()
         call("hrb_lookup_bwd_update", self.plan._h, K._p(ids), ids.stride(0), B, K._p(self.dX0), self.K0p, None, ctypes.byref(op),
              K._p(self._ws_emb), self._ws_emb.numel(), st)
         self._mark("embedding_bwd_update")
@@ -404,9 +436,17 @@ class DeepFMEngine:
             emb_part(side=False)
         self._sync_dense_grads()
         # dense parameters
-        segs = [(0, self.n_params, False)] if self.l2_dnn == 0.0 else self._segments
-        for off, length, reg in segs:
-            l2s = 2.0 * self.l2_dnn if reg else 0.0
+        segs = [(o_, n_, 2.0 * self.l2_dnn if reg else 0.0) for o_, n_, reg in self._segments]
+        if self.n_params > self.n_dense_params:  # dense-updated tables: Keras adds d(l2_embd*sum w^2) for every row (group.py:289)
+            segs.append((self.n_dense_params, self.n_params - self.n_dense_params, 2.0 * self.l2_embd))
+        merged = [segs[0]]
+        for o_, n_, l2_ in segs[1:]:  # neighbouring segments with the same regulariser take one launch
+            po, pn, pl = merged[-1]
+            if pl == l2_ and po + pn == o_:
+                merged[-1] = (po, pn + n_, pl)
+            else:
+                merged.append((o_, n_, l2_))
+        for off, length, l2s in merged:
             o = off * 4
             pp = lambda t: ctypes.c_void_p(t.data_ptr() + o)
             if self.optimizer == "adam":

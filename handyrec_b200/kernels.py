@@ -135,8 +135,8 @@ class LookupPlan:
         td = (TableDesc * len(self.tables))()
         for i, t in enumerate(self.tables):
             td[i].weight = t.data_ptr()
-            td[i].adam_m = self.adam_m[i].data_ptr() if self.adam_m is not None else 0
-            td[i].adam_v = self.adam_v[i].data_ptr() if self.adam_v is not None else 0
+            td[i].adam_m = self.adam_m[i].data_ptr() if self.adam_m is not None and self.adam_m[i] is not None else 0
+            td[i].adam_v = self.adam_v[i].data_ptr() if self.adam_v is not None and self.adam_v[i] is not None else 0
             td[i].rows, td[i].dim = t.shape[0], t.shape[1]
         fd = (FieldDesc * self.n_fields)()
         self.ids_cols = 0
@@ -151,6 +151,13 @@ class LookupPlan:
         with torch.cuda.device(self.device):
             call("hrb_plan_create", td, len(self.tables), fd, self.n_fields, ctypes.byref(self._h))
         self._ws = None
+
+    def set_dense_grads(self, grads: Sequence[Optional[torch.Tensor]]) -> None:
+        """grads[t] (rows, dim) fp32 or None: the backward ADDS table t's row-gradient sums there instead of updating the rows."""
+        assert len(grads) == len(self.tables)
+        self._dense_grads = list(grads)  # keep the buffers alive
+        arr = (ctypes.c_void_p * len(grads))(*[(g.data_ptr() if g is not None else None) for g in grads])
+        call("hrb_plan_set_dense_grads", self._h, arr)
 
     def __del__(self):
         try:  # module globals may already be gone at interpreter shutdown

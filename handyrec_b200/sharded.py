@@ -114,25 +114,38 @@ class TorchDistComm:
     def all_reduce_sum(self, t: torch.Tensor) -> None:
         self.dist.all_reduce(t, group=self.group)
 
-    def alloc_tables(self, vocabs: Sequence[int], dim: int, device) -> Tuple[List[torch.Tensor], Optional[List[List[int]]]]:
+    _dense_group = None
+
+    def all_reduce_dense(self, t: torch.Tensor) -> None:
+        """All-reduce of the replicated parameters' gradients on a communicator of its own (NCCL only), so that it does not
+        queue behind the embedding exchange of the same step on the process group's stream."""
+        if self._dense_group is None:
+            nccl = self.dist.get_backend(self.group) == "nccl"
+            ranks = None if self.group is None else self.dist.get_process_group_ranks(self.group)
+            self._dense_group = self.dist.new_group(ranks=ranks) if nccl else self.group
+        self.dist.all_reduce(t, group=self._dense_group)
+
+    def alloc_tables(self, vocabs: Sequence[int], dim: int, device, replicate_max_rows: int = 0) -> Tuple[List[torch.Tensor], Optional[List[List[int]]]]:
         """Allocate this rank's shards in ONE symmetric-memory arena (torch.distributed._symmetric_memory: CUDA VMM
         allocations exported to every rank of the node and mapped over NVLink) -> (tables, peer_ptrs[r][t]).
-        With the gloo backend (CPU tests) plain tensors are returned and peer_ptrs is None."""
-        rows = [shard_rows(v, self.rank, self.N) for v in vocabs]
+        Tables with at most `replicate_max_rows` rows are not sharded: every rank gets a full copy (plain allocation, peer
+        pointer 0).  With the gloo backend (CPU tests) plain tensors are returned and peer_ptrs is None."""
+        rep = [v <= replicate_max_rows for v in vocabs]
+        rows = [v if r else shard_rows(v, self.rank, self.N) for v, r in zip(vocabs, rep)]
         if self.dist.get_backend(self.group) != "nccl":
             return [torch.zeros(r, dim) for r in rows], None
         import torch.distributed._symmetric_memory as symm_mem
 
-        max_rows = [shard_rows(v, 0, self.N) for v in vocabs]  # identical layout on every rank
         offs, off = [], 0
-        for r in max_rows:
+        for v, r in zip(vocabs, rep):
             offs.append(off)
-            off += (r * dim + 63) // 64 * 64  # 256-byte aligned table starts
-        arena = symm_mem.empty((off,), dtype=torch.float32, device=device)
+            if not r:
+                off += (shard_rows(v, 0, self.N) * dim + 63) // 64 * 64  # identical layout on every rank, 256-byte aligned table starts
+        arena = symm_mem.empty((max(off, 64),), dtype=torch.float32, device=device)
         hdl = symm_mem.rendezvous(arena, group=self.group if self.group is not None else self.dist.group.WORLD)
         self._arena, self._arena_hdl = arena, hdl  # keep the mapping alive
-        tables = [arena[o : o + r * dim].view(r, dim) for o, r in zip(offs, rows)]
-        peer_ptrs = [[int(hdl.buffer_ptrs[rk]) + o * 4 for o in offs] for rk in range(self.N)]
+        tables = [torch.zeros(n, dim, device=device) if r else arena[o : o + n * dim].view(n, dim) for o, n, r in zip(offs, rows, rep)]
+        peer_ptrs = [[0 if r else int(hdl.buffer_ptrs[rk]) + o * 4 for o, r in zip(offs, rep)] for rk in range(self.N)]
         return tables, peer_ptrs
 
 
@@ -175,28 +188,64 @@ class RowExchange:
 
 
 class ShardedDeepFMEngine(DeepFMEngine):
-    """DeepFMEngine with every embedding table row-sharded over the ranks of `comm`.
+    """DeepFMEngine over the ranks of `comm`: large tables row-sharded, small tables replicated.
 
-    `tables` are this rank's SHARDS (rows r with r % N == rank, in order); `vocabs` the full vocabulary sizes.
-    The per-rank batch is fixed (weak scaling); gradients are averaged over the global batch.
+    `vocabs` are the full vocabulary sizes.  `tables[t]` is this rank's SHARD of table t (rows r with r % N == rank, in
+    order) -- or, for t in `replicated` (default: vocab <= `replicate_max_rows`), a full copy that is identical on every
+    rank.  Replicated tables are read locally, their row gradients are reduced into the flat gradient buffer, all-reduced
+    together with the dense parameters' gradients and stepped by the dense optimiser (DeepFMEngine: dense-updated tables);
+    only the sharded tables take part in the row exchange.  The per-rank batch is fixed (weak scaling); gradients are
+    averaged over the global batch.
     """
 
-    def __init__(self, tables, vocabs, fields, n_dense, comm, peer_ptrs=None, **kw):
-        super().__init__(tables, fields, n_dense, **kw)
+    def __init__(self, tables, vocabs, fields, n_dense, comm, peer_ptrs=None, replicate_max_rows: int = 0, replicated=None, **kw):
+        if replicated is None:
+            replicated = [t for t, v in enumerate(vocabs) if v <= replicate_max_rows]
+        self.replicated = sorted(set(int(t) for t in replicated))
+        for t in self.replicated:
+            if tables[t].shape[0] != vocabs[t]:
+                raise ValueError(f"replicated table {t} must be a full copy ({vocabs[t]} rows), got {tables[t].shape[0]}")
+        super().__init__(tables, fields, n_dense, dense_update_tables=self.replicated, **kw)
         self.comm = comm
         self.world = comm.N
-        self.provider = CudaShardProvider(self.plan, vocabs, comm.N, self.B)
-        self.exchange = RowExchange(self.provider, comm)
+        n_t = len(self.tables)
+        self.sharded = [t for t in range(n_t) if t not in self.replicated]
+        # sub-plans over the same id / output matrices: the sharded fields feed the row exchange, the replicated ones the
+        # local gradient reduction
+        def sub_plan(tabs, with_moments):
+            remap = {t: i for i, t in enumerate(tabs)}
+            flds = [(remap[f[0]],) + tuple(f[1:]) for f in self.plan_fields if f[0] in remap]
+            if not flds:
+                return None
+            m = [self.adam_m[t] for t in tabs] if (with_moments and self.adam_m is not None) else None
+            v = [self.adam_v[t] for t in tabs] if (with_moments and self.adam_v is not None) else None
+            return K.LookupPlan([self.tables[t] for t in tabs], flds, m, v)
+
+        if self.replicated:
+            self.plan_shard = sub_plan(self.sharded, True)
+            self.plan_rep = sub_plan(self.replicated, False)
+            if self.plan_rep is not None:
+                self.plan_rep.set_dense_grads([self.table_grads[t] for t in self.replicated])
+                self._ws_rep = torch.empty(self.plan_rep.workspace_bytes(self.B), device=self.dev, dtype=torch.uint8)
+        else:
+            self.plan_shard, self.plan_rep = self.plan, None
+        self.exchange = None
+        if self.plan_shard is not None:
+            self.provider = CudaShardProvider(self.plan_shard, [vocabs[t] for t in self.sharded], comm.N, self.B)
+            self.exchange = RowExchange(self.provider, comm)
         self.grad_scale_div = comm.N
         self.overlap_embedding_bwd = True
         self.peer_lookup = False
-        self._emb_pending = None
+        self._rep_done = None
         self._barrier_buf = torch.zeros(1, device=self.dev)
-        if peer_ptrs is not None and all(f[1] == 1 and f[2] in ("none", None) for f in fields):
+        plain = all(f[1] == 1 and f[2] in ("none", None) for f in fields)
+        if self.exchange is None and plain:
+            self.peer_lookup = True  # everything is replicated: the local fused lookup is the whole forward
+        elif peer_ptrs is not None and plain:
             # forward without any all-to-all: every rank maps every other rank's shards (comm.alloc_tables: symmetric memory over
             # NVLink) and the fused lookup+FM kernel gathers row `id` from rank id % N at local row id // N
-            n_t = len(self.tables)
-            ptrs = (ctypes.c_void_p * (comm.N * n_t))(*[int(peer_ptrs[r][t]) for r in range(comm.N) for t in range(n_t)])
+            ptrs = (ctypes.c_void_p * (comm.N * n_t))(
+                *[(None if t in self.replicated else int(peer_ptrs[r][t])) for r in range(comm.N) for t in range(n_t)])
             full = (ctypes.c_int64 * n_t)(*[int(v) for v in vocabs])
             call("hrb_plan_set_peers", self.plan._h, comm.N, ptrs, full)
             self.peer_lookup = True
@@ -204,34 +253,49 @@ class ShardedDeepFMEngine(DeepFMEngine):
     def _lookup_fm_forward(self, ids, B, st):
         if self.peer_lookup:
             # the routing needed by the BACKWARD exchange depends on the ids only: launch it now, beside the forward
-            main = torch.cuda.current_stream()
-            if self._side is None:
-                self._side = torch.cuda.Stream()
-            if self._marks is None:
-                self._side.wait_stream(main)
-                with torch.cuda.stream(self._side):
+            if self.exchange is not None:
+                main = torch.cuda.current_stream()
+                if self._side is None:
+                    self._side = torch.cuda.Stream()
+                if self._marks is None:
+                    self._side.wait_stream(main)
+                    with torch.cuda.stream(self._side):
+                        self.exchange.route_async(ids)
+                else:
                     self.exchange.route_async(ids)
-            else:
-                self.exchange.route_async(ids)
             super()._lookup_fm_forward(ids, B, st)
             return
-        self.exchange.forward(ids, self.X0)  # the plan's out_col already includes the dense block
+        if self.exchange is not None:
+            self.exchange.forward(ids, self.X0)  # the plan's out_col already includes the dense block
+        if self.plan_rep is not None:
+            call("hrb_lookup_fwd", self.plan_rep._h, K._p(ids), ids.stride(0), B, K._p(self.X0), self.K0p, None, None, st)
         self._mark("sharded_lookup_fwd")
         emb = self.X0[:, self.nd_pad :]
         call("hrb_fm_fwd", K._p(emb), self.K0p, B, self.F, self.D, K._p(self.fm_w), K._p(self.fm_w0), K._p(self.fm_out), K._p(self.fm_sum), st)
         self._mark("fm_fwd")
 
     def _pre_embedding_backward(self):
-        if self.peer_lookup:
+        if self.peer_lookup and self.exchange is not None:
             self.exchange.finish_route()
 
     def _embedding_backward(self, ids, B, st, op):
-        self.exchange.backward_update(ids, self.dX0, op)
-        if self.peer_lookup:
-            # peers read this shard in the next forward: nobody may start it before every rank has finished updating
-            self.comm.all_reduce_sum(self._barrier_buf)
-        self._mark("sharded_embedding_bwd_update")
+        if self.plan_rep is not None:  # replicated tables: local sorted-segment reduction into the flat gradient buffer
+            self._zero_table_grads()
+            call("hrb_lookup_bwd_update", self.plan_rep._h, K._p(ids), ids.stride(0), B, K._p(self.dX0), self.K0p, None, ctypes.byref(op),
+                 K._p(self._ws_rep), self._ws_rep.numel(), st)
+            self._rep_done = torch.cuda.Event()
+            self._rep_done.record()
+            self._mark("replicated_embedding_bwd")
+        if self.exchange is not None:
+            self.exchange.backward_update(ids, self.dX0, op)
+            if self.peer_lookup:
+                # peers read this shard in the next forward: nobody may start it before every rank has finished updating
+                self.comm.all_reduce_sum(self._barrier_buf)
+            self._mark("sharded_embedding_bwd_update")
 
     def _sync_dense_grads(self):
-        self.comm.all_reduce_sum(self.grads)
+        if self._rep_done is not None:  # recorded on the side stream when the embedding backward is overlapped
+            torch.cuda.current_stream().wait_event(self._rep_done)
+            self._rep_done = None
+        getattr(self.comm, "all_reduce_dense", self.comm.all_reduce_sum)(self.grads)
         self._mark("dense_allreduce")

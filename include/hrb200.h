@@ -155,6 +155,13 @@ int hrb_lookup_bwd_update(const hrb_plan* plan, const int32_t* ids, int64_t ids_
                           const hrb_opt_params* opt_host, void* workspace, size_t workspace_bytes,
                           void* stream);
 
+/* Dense-updated tables: grads_host[t] != NULL (rows*dim fp32, 16-byte aligned) makes hrb_lookup_bwd_update ADD the
+ * per-row gradient sums of table t into that buffer and leave weight/moments alone -- the caller zeroes the buffer,
+ * (all-reduces it when the table is replicated over ranks) and runs its dense optimiser step over the table, which is
+ * exactly what Keras does for an IndexedSlices gradient under Adam (dense moment decay).  NULL keeps the in-place
+ * touched-rows update.  The array has n_tables entries. */
+int hrb_plan_set_dense_grads(hrb_plan* plan, float* const* grads_host);
+
 /* ------------------------------------------------------------------------------------------
  * a9  FM.call   (layers/interaction.py:15-39) on a materialised (B,F,D) tensor.
  *   x rows are x_ld floats apart (x_ld >= F*D).  out (B).  fm_sum (nullable) (B,D).
@@ -304,7 +311,8 @@ int hrb_lookup_combine(const hrb_plan* plan, const float* psum, const float* pco
 /* Peer-mapped lookup: peer_tables_host[r*n_tables + t] = device pointer of rank r's shard of table t as mapped into this
  * process (CUDA IPC / symmetric memory over NVLink), full_rows_host[t] = full vocabulary size.  After this call
  * hrb_lookup_fwd / hrb_lookup_fm_fwd take GLOBAL ids and read row id from rank id % n_ranks at local row id / n_ranks:
- * the forward needs no all-to-all (plain-lookup groups laid out contiguously only). */
+ * the forward needs no all-to-all (plain-lookup groups laid out contiguously only).  A table whose pointers are NULL on
+ * EVERY rank is replicated: its rows are read from the plan's own copy (hrb_table_desc.weight, full row count). */
 int hrb_enable_peer_access(int32_t peer_device); /* cudaDeviceEnablePeerAccess from the current device, idempotent */
 int hrb_plan_set_peers(hrb_plan* plan, int32_t n_ranks, const void* const* peer_tables_host, const int64_t* full_rows_host);
 int hrb_route_workspace(const hrb_plan* plan, int64_t batch, size_t* bytes);

@@ -93,6 +93,45 @@ def test_engine_adam_and_host_api(dev):
     assert pr.shape == (B, 1) and float(pr.min()) > 0 and float(pr.max()) < 1
 
 
+@pytest.mark.parametrize("optimizer", ["adam", "sgd"])
+def test_engine_dense_updated_tables(dev, optimizer):
+    """Tables <= dense_table_max_rows take the dense (Keras) optimiser step -- moment decay and l2_embd on EVERY row --
+    while larger tables keep the touched-rows-only update.  Two steps on different batches tell the two apart."""
+    from handyrec_b200.engine import DeepFMEngine
+
+    B, D, n_dense, hidden, lr, l2 = 64, 8, 2, (8, 1), 0.05, 0.01
+    vocabs = [7, 50, 1000]
+    tables = [rnd(v, D, seed=20 + i, scale=0.05) for i, v in enumerate(vocabs)]
+    fields = [(0, 1, "none"), (1, 1, "none"), (2, 1, "none")]
+    eng = DeepFMEngine([t.clone().to(dev) for t in tables], fields, n_dense, hidden, "relu", batch_size=B, optimizer=optimizer, lr=lr, l2_embd=l2,
+                       dense_table_max_rows=50)
+    assert eng.dense_tables == [0, 1]
+    m = [torch.zeros_like(t) for t in tables]
+    v = [torch.zeros_like(t) for t in tables]
+    cur = [t.clone() for t in tables]
+    for step in (1, 2):
+        g = torch.Generator().manual_seed(100 + step)
+        ids = torch.cat([torch.randint(0, vv, (B, 1), generator=g, dtype=torch.int32) for vv in vocabs], 1)
+        dense, label = rnd(B, n_dense, seed=step), (torch.rand(B, generator=g) < 0.3).float()
+        leaf, *_ = _oracle_step(eng, cur, fields, ids, dense, label, B, hidden)
+        eng.train_step_on_device(ids.to(dev), dense.to(dev), label.to(dev))
+        lr_t = lr * np.sqrt(1 - 0.999 ** step) / (1 - 0.9 ** step)
+        for t in range(3):
+            touched = torch.zeros(vocabs[t], dtype=torch.bool)
+            touched[ids[:, t].long()] = True
+            rows = torch.ones_like(touched) if t in eng.dense_tables else touched
+            gt = (leaf[t].grad + 2 * l2 * cur[t]) * rows[:, None]
+            if optimizer == "sgd":
+                cur[t] = cur[t] - lr * gt
+            else:
+                m_new, v_new = 0.9 * m[t] + 0.1 * gt, 0.999 * v[t] + 0.001 * gt * gt
+                m[t] = torch.where(rows[:, None], m_new, m[t])
+                v[t] = torch.where(rows[:, None], v_new, v[t])
+                cur[t] = torch.where(rows[:, None], cur[t] - lr_t * m[t] / (v[t].sqrt() + 1e-7), cur[t])
+            close(eng.tables[t], cur[t], 2e-4)
+        cur = [t_.cpu().clone() for t_ in eng.tables]  # the next oracle step starts from the engine's state
+
+
 def test_engine_rejects_bad_configs(dev):
     from handyrec_b200.engine import DeepFMEngine
 

@@ -68,9 +68,12 @@ def test_row_exchange_cuda(dev, world, opt):
                 close(s[: ws.shape[0]], ws, 1e-4)
 
 
-@pytest.mark.parametrize("world,b,peer", [(2, 64, True), (4, 64, False), (2, 512, True), (2, 512, False), (8, 64, True)])
-def test_sharded_engine_matches_single_gpu_engine(dev, world, b, peer):
-    """N emulated ranks with row-sharded tables take the same SGD step as one engine on the concatenated batch."""
+@pytest.mark.parametrize("world,b,peer,rep,opt", [(2, 64, True, 0, "sgd"), (4, 64, False, 0, "sgd"), (2, 512, True, 0, "sgd"), (2, 512, False, 0, "sgd"),
+                                                  (8, 64, True, 0, "sgd"), (2, 512, True, 60, "adam"), (4, 64, False, 60, "adam"), (2, 64, True, 60, "sgd"),
+                                                  (2, 512, True, 1000, "adam")])
+def test_sharded_engine_matches_single_gpu_engine(dev, world, b, peer, rep, opt):
+    """N emulated ranks (large tables row-sharded, tables <= rep rows replicated) take the same step as one engine on the
+    concatenated batch."""
     from handyrec_b200 import kernels as K
     from handyrec_b200.engine import DeepFMEngine
     from handyrec_b200.sharded import ShardedDeepFMEngine
@@ -83,19 +86,20 @@ def test_sharded_engine_matches_single_gpu_engine(dev, world, b, peer):
     ids = [torch.stack([torch.randint(0, v, (b,), generator=g, dtype=torch.int32) for v in vocabs], 1) for _ in range(world)]
     dense = [torch.randn(b, n_dense, generator=g) for _ in range(world)]
     label = [(torch.rand(b, generator=g) < 0.3).float() for _ in range(world)]
-    ref = DeepFMEngine([t.clone().to(dev) for t in tables], fields, n_dense, hidden, "relu", batch_size=b * world, optimizer="sgd", lr=0.1, seed=7)
+    ref = DeepFMEngine([t.clone().to(dev) for t in tables], fields, n_dense, hidden, "relu", batch_size=b * world, optimizer=opt, lr=0.1, seed=7,
+                       dense_table_max_rows=rep)
     ref.train_step_on_device(torch.cat(ids).to(dev), torch.cat(dense).to(dev), torch.cat(label).to(dev))
     torch.cuda.synchronize()
     shared = H.ThreadComm.Shared(world)
     engines = [None] * world
 
     def rank_fn(r):
-        sh = [t.to(dev) for t in H.shards_of(tables, r, world)]
+        sh = [(full if v <= rep else s_).to(dev) for full, s_, v in zip(tables, H.shards_of(tables, r, world), vocabs)]
         comm = H.ThreadComm(shared, r)
         peer_ptrs = comm.share_ptrs(sh) if peer else None  # peer-mapped forward (no all-to-all) vs. row-exchange forward
         eng = ShardedDeepFMEngine(sh, vocabs, fields, n_dense, comm, peer_ptrs=peer_ptrs, dnn_hidden_units=hidden, dnn_activation="relu",
-                                  batch_size=b, optimizer="sgd", lr=0.1, seed=7)
-        assert eng.peer_lookup == peer
+                                  batch_size=b, optimizer=opt, lr=0.1, seed=7, replicate_max_rows=rep)
+        assert eng.peer_lookup == peer or rep >= 1000
         engines[r] = eng
         eng.train_step_on_device(ids[r].to(dev), dense[r].to(dev), label[r].to(dev))
         torch.cuda.synchronize()
@@ -106,6 +110,6 @@ def test_sharded_engine_matches_single_gpu_engine(dev, world, b, peer):
     for r in range(world):
         close(engines[r].params, ref.params, 1e-4)  # replicated dense parameters stay identical after the all-reduce
         for t in range(len(vocabs)):
-            ws = ref.tables[t][r::world]
+            ws = ref.tables[t] if vocabs[t] <= rep else ref.tables[t][r::world]
             if ws.shape[0]:
                 close(engines[r].tables[t][: ws.shape[0]], ws, 1e-4)

@@ -302,6 +302,11 @@ def main():
     torch.cuda.synchronize()
     lookup_alone_ms = a.elapsed_time(b) / reps
 
+    timeline = None
+    if world > 1:  # completion time of every phase of a production step (side streams running), ms since the step started
+        barrier()
+        timeline = eng.timeline_step(ids_pool[0], dense_pool[0], label_pool[0])
+        barrier()
     if rank != 0:
         return
     step_ms = ms / args.steps
@@ -369,6 +374,8 @@ def main():
         "clocks": clk, "roofline": roofline, "roofline_lookup": rl_lookup, "roofline_embedding_bwd": rl_emb, "cpu_baseline": cpu,
         "kernel_ms": {k: round(v, 4) for k, v in phases.items()},
     }
+    if timeline is not None:
+        line["timeline_ms"] = timeline
     print(json.dumps(line), flush=True)
 
 

@@ -193,7 +193,13 @@ class DeepFMEngine:
     # ------------------------------------------------------------------------------------------
     _marks = None  # when a list: (phase name, cuda event) recorded after every phase of a step
 
+    _timeline = None  # when a list: (name, event) recorded on whatever stream is current, WITHOUT serialising the streams
+
     def _mark(self, name: str) -> None:
+        if self._timeline is not None:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            self._timeline.append((name, e))
         if self._marks is not None:
             e = torch.cuda.Event(enable_timing=True)
             e.record()
@@ -212,6 +218,21 @@ class DeepFMEngine:
         for (n0, e0), (n1, e1) in zip(marks[:-1], marks[1:]):
             out[n1] = out.get(n1, 0.0) + e0.elapsed_time(e1)
         return out
+
+    def timeline_step(self, ids, dense, label) -> "OrderedDict[str, float]":
+        """One NORMAL step (side streams and overlap as in production) with an event after every phase on the stream the
+        phase runs on; returns the completion time of every phase in ms since the start of the step."""
+        from collections import OrderedDict
+
+        torch.cuda.synchronize()
+        self._timeline = []
+        self._mark("start")
+        self.train_step_on_device(ids, dense, label)
+        self._mark("end")
+        torch.cuda.synchronize()
+        tl, self._timeline = self._timeline, None
+        e0 = tl[0][1]
+        return OrderedDict((n, round(e0.elapsed_time(e), 4)) for n, e in tl[1:])
 
     def _refresh_wt(self) -> None:
         """W_i^T for the tensor-core forward (the optimiser updates W_i; 1.3 MB of transposes per step)."""

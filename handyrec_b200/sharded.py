@@ -111,6 +111,12 @@ class TorchDistComm:
         self.dist.all_to_all_single(recv, send, output_split_sizes=recv_counts, input_split_sizes=send_counts, group=self.group)
         return recv
 
+    def all_to_all_v_start(self, send: torch.Tensor, send_counts: List[int], recv_counts: List[int]):
+        """Non-blocking variant: -> (recv, wait) where wait() makes the CURRENT stream wait for the transfer."""
+        recv = torch.empty((sum(recv_counts),) + tuple(send.shape[1:]), device=send.device, dtype=send.dtype)
+        work = self.dist.all_to_all_single(recv, send, output_split_sizes=recv_counts, input_split_sizes=send_counts, group=self.group, async_op=True)
+        return recv, work.wait
+
     def all_reduce_sum(self, t: torch.Tensor) -> None:
         self.dist.all_reduce(t, group=self.group)
 
@@ -180,11 +186,30 @@ class RowExchange:
         got = self.comm.all_to_all_v(rows, self.recv_counts, self.send_counts)
         self.p.scatter_rows(ids, self.perm, self.n_send, got, out)
 
-    def backward_update(self, ids: torch.Tensor, dout: torch.Tensor, op) -> None:
+    def backward_start(self, ids: torch.Tensor, dout: torch.Tensor) -> None:
+        """Gather this rank's per-position gradient rows and put them on the wire; work issued to the current stream after
+        this call overlaps the transfer."""
         self.finish_route()
-        send = self.p.gather_grads(ids, self.perm, self.n_send, dout)
-        recv = self.comm.all_to_all_v(send, self.send_counts, self.recv_counts)
-        self.p.keyed_update(self.recv_keys, recv, self.n_recv, op)
+        self._grad_send = self.p.gather_grads(ids, self.perm, self.n_send, dout)
+        start = getattr(self.comm, "all_to_all_v_start", None)
+        if start is not None:
+            self._grad_recv, self._grad_wait = start(self._grad_send, self.send_counts, self.recv_counts)
+        else:
+            self._grad_recv, self._grad_wait = self.comm.all_to_all_v(self._grad_send, self.send_counts, self.recv_counts), None
+
+    def backward_finish(self, op, mark=None) -> None:
+        if self._grad_wait is not None:
+            self._grad_wait()
+        if mark is not None:
+            mark("grad_rows_all_to_all")
+        self.p.keyed_update(self.recv_keys, self._grad_recv, self.n_recv, op)
+        self._grad_send = self._grad_recv = self._grad_wait = None
+        if mark is not None:
+            mark("keyed_update")
+
+    def backward_update(self, ids: torch.Tensor, dout: torch.Tensor, op, mark=None) -> None:
+        self.backward_start(ids, dout)
+        self.backward_finish(op, mark)
 
 
 class ShardedDeepFMEngine(DeepFMEngine):
@@ -252,7 +277,9 @@ class ShardedDeepFMEngine(DeepFMEngine):
 
     def _lookup_fm_forward(self, ids, B, st):
         if self.peer_lookup:
-            # the routing needed by the BACKWARD exchange depends on the ids only: launch it now, beside the forward
+            super()._lookup_fm_forward(ids, B, st)
+            # the routing needed by the BACKWARD exchange depends on the ids only: it is issued right behind the lookup, on the side
+            # stream, so that it fills in beside the dense forward instead of delaying the lookup
             if self.exchange is not None:
                 main = torch.cuda.current_stream()
                 if self._side is None:
@@ -263,7 +290,7 @@ class ShardedDeepFMEngine(DeepFMEngine):
                         self.exchange.route_async(ids)
                 else:
                     self.exchange.route_async(ids)
-            super()._lookup_fm_forward(ids, B, st)
+                    self._mark("route_ids")
             return
         if self.exchange is not None:
             self.exchange.forward(ids, self.X0)  # the plan's out_col already includes the dense block
@@ -277,8 +304,12 @@ class ShardedDeepFMEngine(DeepFMEngine):
     def _pre_embedding_backward(self):
         if self.peer_lookup and self.exchange is not None:
             self.exchange.finish_route()
+            if self._timeline is not None:
+                self._mark("route_keys_all_to_all")
 
     def _embedding_backward(self, ids, B, st, op):
+        if self.exchange is not None:  # gradient rows of the sharded tables go on the wire first: the transfer runs beside the local reduction
+            self.exchange.backward_start(ids, self.dX0)
         if self.plan_rep is not None:  # replicated tables: local sorted-segment reduction into the flat gradient buffer
             self._zero_table_grads()
             call("hrb_lookup_bwd_update", self.plan_rep._h, K._p(ids), ids.stride(0), B, K._p(self.dX0), self.K0p, None, ctypes.byref(op),
@@ -287,7 +318,7 @@ class ShardedDeepFMEngine(DeepFMEngine):
             self._rep_done.record()
             self._mark("replicated_embedding_bwd")
         if self.exchange is not None:
-            self.exchange.backward_update(ids, self.dX0, op)
+            self.exchange.backward_finish(op, mark=self._mark if self._timeline is not None else None)
             if self.peer_lookup:
                 # peers read this shard in the next forward: nobody may start it before every rank has finished updating
                 self.comm.all_reduce_sum(self._barrier_buf)

@@ -19,6 +19,7 @@
 // Pipelines: full (TMA->conv), conv (conv->MMA), empty (MMA->TMA, tcgen05.commit), tmem_full / tmem_empty.
 #include <cuda.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 
@@ -27,7 +28,8 @@ namespace tc {
 
 constexpr int BM = 128;
 constexpr int BK = 32;  // 32 fp32 = 128 bytes = one SWIZZLE_128B span
-constexpr int STAGES = 3;
+constexpr int STAGES_SMEM_A = 3;  // A hi/lo in shared memory: 64 KB per stage
+constexpr int STAGES_TMEM_A = 4;  // A hi/lo in tensor memory: 48 KB per stage, 64 TMEM columns per stage
 constexpr int THREADS = 512;
 constexpr int EPI_WARP0 = 4, CONV_WARP0 = 8;
 constexpr int CONV_THREADS = 256;
@@ -84,6 +86,20 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// A operand read from tensor memory (lane = row of the 128-row tile, one 32-bit column per tf32 element)
+__device__ __forceinline__ void umma_tf32_ta(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]),
+      "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s32(bar)) : "memory");
 }
@@ -119,14 +135,25 @@ struct Args {
   int32_t debug;       // HRB_TC_DEBUG bit mask (perf experiments only): 1 no stores, 2 no conversion, 4 no MMA, 8 no TMA, 16 also write hi back
 };
 
-template <int BN, int EPI>
+// ATM: the A tile's hi/lo halves live in TENSOR MEMORY (written by the converter warps with tcgen05.st) instead of shared
+// memory.  The kernel is bound by shared-memory bandwidth (TMA writes + converter read/write + 6 operand-tile reads per
+// k-block by the three MMAs, ~245 B/clk wanted against 128 B/clk): with A in TMEM the MMAs read only B from shared memory
+// and the converter no longer writes A_lo there (-36 % shared-memory traffic per k-block).
+template <int BN, int EPI, bool ATM>
 __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a,
                                                              const __grid_constant__ CUtensorMap map_b,
                                                              const __grid_constant__ CUtensorMap map_c,
                                                              const __grid_constant__ CUtensorMap map_ct, Args g) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
+  constexpr int STAGES = ATM ? STAGES_TMEM_A : STAGES_SMEM_A;
   constexpr uint32_t A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4;
-  constexpr uint32_t STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;  // A_hi | A_lo | B_hi | B_lo
+  constexpr uint32_t B_OFF = ATM ? A_BYTES : 2 * A_BYTES;
+  constexpr uint32_t STAGE_BYTES = B_OFF + 2 * B_BYTES;  // A (raw = hi) | [A_lo] | B (raw = hi) | B_lo
+  constexpr uint32_t ACC_COLS = 2 * BN;                  // two accumulator stages
+  constexpr uint32_t A_COLS = 2 * BK;                    // ATM: per stage, hi columns then lo columns
+  constexpr uint32_t TMEM_NEED = ACC_COLS + (ATM ? STAGES * A_COLS : 0);
+  constexpr uint32_t TMEM_COLS = TMEM_NEED <= 32 ? 32 : TMEM_NEED <= 64 ? 64 : TMEM_NEED <= 128 ? 128 : TMEM_NEED <= 256 ? 256 : 512;
+  static_assert(TMEM_NEED <= 512, "tensor memory budget");
   // 1024-byte alignment of every tile (SWIZZLE_128B atoms are 8 rows x 128 B)
   // (pointer arithmetic on the __shared__ array keeps the address space known: LDS/STS, not generic LD/ST)
   unsigned char* tiles = smem_raw + ((1024u - (s32(smem_raw) & 1023u)) & 1023u);
@@ -150,9 +177,8 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 2) {  // one warp allocates 2 accumulator stages (power of two >= 32 columns)
-    constexpr uint32_t cols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(&tmem_base_smem)), "n"(cols) : "memory");
+  if (warp == 2) {  // one warp allocates 2 accumulator stages (+ the A stages), a power of two >= 32 columns
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(&tmem_base_smem)), "n"(TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
@@ -186,7 +212,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
           }
           mbar_expect_tx(&full_bar[s], A_BYTES + B_BYTES);
           tma_load_2d(st, &map_a, &full_bar[s], kb * BK, mt * BM);
-          tma_load_2d(st + 2 * A_BYTES, &map_b, &full_bar[s], kb * BK, nt * BN);
+          tma_load_2d(st + B_OFF, &map_b, &full_bar[s], kb * BK, nt * BN);
         }
       }
     }
@@ -210,15 +236,27 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
           mbar_wait(&conv_bar[s], (it / STAGES) & 1);
           tc_fence_after();
           unsigned char* st = tiles + (size_t)s * STAGE_BYTES;
-          const uint64_t a_hi = make_desc(st), a_lo = make_desc(st + A_BYTES);
-          const uint64_t b_hi = make_desc(st + 2 * A_BYTES), b_lo = make_desc(st + 2 * A_BYTES + B_BYTES);
-          if (!(g.debug & 4))
+          const uint64_t b_hi = make_desc(st + B_OFF), b_lo = make_desc(st + B_OFF + B_BYTES);
+          if (ATM) {
+            const uint32_t ta_hi = tmem_base + ACC_COLS + (uint32_t)s * A_COLS, ta_lo = ta_hi + BK;
+            if (!(g.debug & 4))
 #pragma unroll
-          for (int kk = 0; kk < BK / 8; ++kk) {  // UMMA_K = 8 tf32 = 32 bytes: +2 in the (>>4) start-address field
-            const uint64_t o = (uint64_t)(kk * 2);
-            umma_tf32(tmem_d, a_lo + o, b_hi + o, idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
-            umma_tf32(tmem_d, a_hi + o, b_lo + o, idesc, 1u);
-            umma_tf32(tmem_d, a_hi + o, b_hi + o, idesc, 1u);
+            for (int kk = 0; kk < BK / 8; ++kk) {  // UMMA_K = 8 tf32: 8 TMEM columns of A, 32 bytes of B
+              const uint64_t o = (uint64_t)(kk * 2);
+              umma_tf32_ta(tmem_d, ta_lo + kk * 8, b_hi + o, idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
+              umma_tf32_ta(tmem_d, ta_hi + kk * 8, b_lo + o, idesc, 1u);
+              umma_tf32_ta(tmem_d, ta_hi + kk * 8, b_hi + o, idesc, 1u);
+            }
+          } else {
+            const uint64_t a_hi = make_desc(st), a_lo = make_desc(st + A_BYTES);
+            if (!(g.debug & 4))
+#pragma unroll
+            for (int kk = 0; kk < BK / 8; ++kk) {  // UMMA_K = 8 tf32 = 32 bytes: +2 in the (>>4) start-address field
+              const uint64_t o = (uint64_t)(kk * 2);
+              umma_tf32(tmem_d, a_lo + o, b_hi + o, idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
+              umma_tf32(tmem_d, a_hi + o, b_lo + o, idesc, 1u);
+              umma_tf32(tmem_d, a_hi + o, b_hi + o, idesc, 1u);
+            }
           }
           umma_commit(&empty_bar[s]);  // frees the smem stage once these MMAs retire
         }
@@ -237,6 +275,31 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
         const int s = it % STAGES;
         mbar_wait(&full_bar[s], (it / STAGES) & 1);
         unsigned char* st = tiles + (size_t)s * STAGE_BYTES;
+        if (ATM) {
+          // A: this thread owns row (warp%4)*32+lane of the tile (the TMEM lanes its warp may touch) and 16 of the 32 k-columns;
+          // row r of a SWIZZLE_128B tile keeps its 16-byte chunk c at chunk c ^ (r % 8)
+          if (!(g.debug & 2)) {
+            const int qrow = warp & 3, half = (warp - CONV_WARP0) >> 2;
+            const int row = qrow * 32 + lane;
+            const float4* src = reinterpret_cast<const float4*>(st + row * 128);
+            uint32_t hi[16], lo[16];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const float4 x = src[(half * 4 + c) ^ (row & 7)];
+              const float xs[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const uint32_t h = __float_as_uint(xs[j]) & 0xFFFFE000u;
+                hi[c * 4 + j] = h;
+                lo[c * 4 + j] = __float_as_uint(xs[j] - __uint_as_float(h));
+              }
+            }
+            const uint32_t ta = tmem_base + ((uint32_t)(qrow * 32) << 16) + ACC_COLS + (uint32_t)s * A_COLS + (uint32_t)(half * 16);
+            tmem_st16(ta, hi);
+            tmem_st16(ta + BK, lo);
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+          }
+        } else {
         // element-wise, so the swizzled placement is irrelevant: lo lands at the same offset as hi
         if (!(g.debug & 2))
 #pragma unroll 4
@@ -250,18 +313,20 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
           if (g.debug & 16) *p = h;  // the MMA reads only the TF32 bits of the raw fp32 operand: writing hi back is redundant
           reinterpret_cast<float4*>(st + A_BYTES)[i] = make_float4(x.x - h.x, x.y - h.y, x.z - h.z, x.w - h.w);
         }
+        }
         if (!(g.debug & 2))
 #pragma unroll 4
         for (int i = t; i < (int)(B_BYTES / 16); i += CONV_THREADS) {
-          float4* p = reinterpret_cast<float4*>(st + 2 * A_BYTES) + i;
+          float4* p = reinterpret_cast<float4*>(st + B_OFF) + i;
           float4 x = *p, h;
           h.x = __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u);
           h.y = __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u);
           h.z = __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u);
           h.w = __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u);
           if (g.debug & 16) *p = h;  // the MMA reads only the TF32 bits of the raw fp32 operand: writing hi back is redundant
-          reinterpret_cast<float4*>(st + 2 * A_BYTES + B_BYTES)[i] = make_float4(x.x - h.x, x.y - h.y, x.z - h.z, x.w - h.w);
+          reinterpret_cast<float4*>(st + B_OFF + B_BYTES)[i] = make_float4(x.x - h.x, x.y - h.y, x.z - h.z, x.w - h.w);
         }
+        if (ATM) tc_fence_before();  // the tcgen05.st above are ordered before the MMA issuer's tcgen05.mma by the barrier
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to UMMA
         mbar_arrive(&conv_bar[s]);
       }
@@ -371,8 +436,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
   tc_fence_before();
   __syncthreads();
   if (warp == 2) {
-    constexpr uint32_t cols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(cols) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
   }
 }
 
@@ -445,15 +509,26 @@ static int launch(const float* A, int64_t lda, const float* Bt, int64_t ldb, con
   } else {
     mct = mc;
   }
-  constexpr size_t smem = (size_t)STAGES * (2 * BM * BK * 4 + 2 * BN * BK * 4) + 2 * STAGE_C_BYTES + 1024;
+  static int a_tmem = -1;  // HRB_TC_A=smem keeps the A tile's hi/lo halves in shared memory (the first version of the kernel)
+  if (a_tmem < 0) {
+    const char* e = getenv("HRB_TC_A");
+    a_tmem = (e != nullptr && strcmp(e, "smem") == 0) ? 0 : 1;
+  }
+  constexpr size_t smem_s = (size_t)STAGES_SMEM_A * (2 * BM * BK * 4 + 2 * BN * BK * 4) + 2 * STAGE_C_BYTES + 1024;
+  constexpr size_t smem_t = (size_t)STAGES_TMEM_A * (BM * BK * 4 + 2 * BN * BK * 4) + 2 * STAGE_C_BYTES + 1024;
+  static_assert(smem_s <= 227 * 1024 && smem_t <= 227 * 1024, "shared memory budget");
   static bool attr_done = false;
   if (!attr_done) {
-    HRB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    HRB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s));
+    HRB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t));
     attr_done = true;
   }
   const int64_t work = (int64_t)((g.M + BM - 1) / BM) * ((g.N + BN - 1) / BN) * g.splits;
   int64_t grid = work < sm_count() ? work : sm_count();
-  gemm_tc_kernel<BN, EPI><<<(unsigned)grid, THREADS, smem, st>>>(ma, mb, mc, mct, g);
+  if (a_tmem)
+    gemm_tc_kernel<BN, EPI, true><<<(unsigned)grid, THREADS, smem_t, st>>>(ma, mb, mc, mct, g);
+  else
+    gemm_tc_kernel<BN, EPI, false><<<(unsigned)grid, THREADS, smem_s, st>>>(ma, mb, mc, mct, g);
   HRB_LAUNCH_CHECK();
   return HRB_OK;
 }

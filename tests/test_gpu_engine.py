@@ -76,7 +76,7 @@ def test_engine_adam_and_host_api(dev):
     eng, tables, fields, ids, dense, label = _setup(dev, B, D, n_dense, hidden, "adam")
     leaf, p, fm_w, fm_w0, logit, loss = _oracle_step(eng, tables, fields, ids, dense, label, B, hidden)
     got = eng.train_on_batch(ids.pin_memory(), dense.pin_memory(), label.pin_memory())
-    assert abs(got - float(loss)) <= 1e-5 * max(1.0, abs(float(loss)))
+    assert abs(got - float(loss.detach())) <= 1e-5 * max(1.0, abs(float(loss.detach())))
     lr_t = 0.05 * np.sqrt(1 - 0.999) / (1 - 0.9)
     for i in range(len(eng.units)):
         g = p.W[i].grad

@@ -380,7 +380,7 @@ int hrb_tc_gemm_act_grad(const float* a, int64_t lda, const float* bt, int64_t l
                          cudaStream_t st);
 int hrb_tc_splits(int64_t M, int32_t N, int32_t K);
 int hrb_tc_gemm_splitk(const float* a, int64_t lda, const float* bt, int64_t ldb, int64_t M, int32_t N, int32_t K, int32_t splits,
-                       float* part, int64_t ldp, cudaStream_t st);
+                       float* part, int64_t ldp, float* bsum, cudaStream_t st);
 int hrb_tc_dense_fwd(const float* x, int64_t ldx, const float* w, int64_t ldw, const float* bias, int64_t M, int32_t K,
                      int32_t N, int32_t act, float* y, int64_t ldy, cudaStream_t st);
 int hrb_tc_dense_bwd_x(const float* dz, int64_t lddz, const float* w, int64_t ldw, int64_t M, int32_t K, int32_t N,
@@ -531,7 +531,8 @@ HRB_API int hrb_dense_bwd_w_t(const float* xt, int64_t ldxt, const float* dzt, i
                               int32_t K, int32_t N, float* dw, int64_t lddw, float* dbias, void* workspace, size_t workspace_bytes,
                               void* stream) {
   HRB_REQUIRE(xt && dzt && dw && workspace && M > 0 && K > 0 && N > 0 && ldxt >= M && lddzt >= M && lddw >= N, "hrb_dense_bwd_w_t: bad argument");
-  HRB_REQUIRE(dbias == nullptr || (dz != nullptr && lddz >= N), "hrb_dense_bwd_w_t: dbias needs dz");
+  (void)dz;
+  (void)lddz;  // kept in the signature: the column sums now come from dz^T inside the GEMM
   HRB_REQUIRE(M <= 0x7fffffff, "hrb_dense_bwd_w_t: M too large");
   size_t need = 0;
   hrb_dense_bwd_w_t_workspace(M, K, N, &need);
@@ -541,17 +542,14 @@ HRB_API int hrb_dense_bwd_w_t(const float* xt, int64_t ldxt, const float* dzt, i
   const int64_t ldp = (N + 3) / 4 * 4;
   float* part = (float*)workspace;
   float* colpart = part + (size_t)splits * K * ldp;
-  int rc = hrb_tc_gemm_splitk(xt, ldxt, dzt, lddzt, K, N, (int32_t)M, splits, part, ldp, st);
+  // the bias gradient (column sums of dz = row sums of dz^T) rides along in the GEMM: its converter warps touch every element
+  // of the dz^T tiles anyway and leave one partial sum per (split, column)
+  int rc = hrb_tc_gemm_splitk(xt, ldxt, dzt, lddzt, K, N, (int32_t)M, splits, part, ldp, dbias != nullptr ? colpart : nullptr, st);
   if (rc != HRB_OK) return rc;
   launch_split_reduce(part, K, N, ldp, splits, dw, lddw, st);
   HRB_LAUNCH_CHECK();
   if (dbias != nullptr) {
-    int yb = (int)min((int64_t)256, (M + 255) / 256);
-    const int64_t rpb = (M + yb - 1) / yb;
-    dim3 grid((N + 31) / 32, yb);
-    colsum_partial_kernel<<<grid, 256, 0, st>>>(dz, lddz, M, N, rpb, colpart);
-    HRB_LAUNCH_CHECK();
-    launch_split_reduce(colpart, 1, N, N, yb, dbias, N, st);
+    launch_split_reduce(colpart, 1, N, N, splits, dbias, N, st);
     HRB_LAUNCH_CHECK();
   }
   return HRB_OK;

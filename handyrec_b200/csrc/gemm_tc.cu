@@ -209,7 +209,7 @@ struct Args {
 // converter and epilogue warps arrive on the leader's barriers through the cluster address space.  Per CTA and k-block this moves
 // 24 KB instead of 32 KB from L2 and 80 KB instead of 128 KB through shared memory.
 #define HRB_TRACE(role, it_) \
-  if (g.trace != nullptr && blockIdx.x < 2 && (it_) < 64) g.trace[((blockIdx.x * 5 + (role)) << 6) + (it_)] = clock64();
+  if (g.trace != nullptr && blockIdx.x < 2 && (it_) < 64) g.trace[((blockIdx.x * 8 + (role)) << 6) + (it_)] = clock64();
 
 template <int BN, int EPI, bool ATM, bool PAIR>
 __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a,
@@ -327,6 +327,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
         else
           mbar_wait(&tempty_bar[a], ((tcount >> 1) & 1) ^ 1);  // epilogue drained this accumulator
         tc_fence_after();
+        if (lane == 0) { HRB_TRACE(7, tcount) }
         const uint32_t tmem_d = tmem_base + (uint32_t)(a * BN);
         for (int kb = kb0; kb < kb1; ++kb, ++it) {
           const int s = it % STAGES;
@@ -492,6 +493,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
       const int a = tcount & 1;
       mbar_wait(&tfull_bar[a], (tcount >> 1) & 1);
       tc_fence_after();
+      if (et == 0) { HRB_TRACE(5, tcount) }
       const int64_t m = (int64_t)mt * BMT + (int64_t)pair_rank * BM + et;
       const int m_row0 = mt * BMT + (int)pair_rank * BM;
       const bool row_ok = m < g.M;
@@ -585,6 +587,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
         }
       }
       tc_fence_before();
+      if (et == 0) { HRB_TRACE(6, tcount) }
       __syncwarp();
       if (lane == 0) {
         if (PAIR && !leader)
@@ -658,15 +661,15 @@ static void dump_trace(long long* d_trace, cudaStream_t st) {
   static int dumped = 0;
   if (d_trace == nullptr || dumped >= 2) return;
   ++dumped;
-  static long long h[2 * 5 * 64];
+  static long long h[2 * 8 * 64];
   cudaStreamSynchronize(st);
   cudaMemcpy(h, d_trace, sizeof(h), cudaMemcpyDeviceToHost);
-  const char* names[5] = {"tma_issue", "conv_full", "conv_done", "mma_ready", "mma_commit"};
+  const char* names[8] = {"tma_issue", "conv_full", "conv_done", "mma_ready", "mma_commit", "epi_start", "epi_end", "mma_tile"};
   for (int c = 0; c < 2; ++c) {
-    const long long t0 = h[(c * 5 + 0) << 6];
-    for (int r = 0; r < 5; ++r) {
+    const long long t0 = h[(c * 8 + 0) << 6];
+    for (int r = 0; r < 8; ++r) {
       fprintf(stderr, "cta%d %-10s", c, names[r]);
-      for (int i = 0; i < 40; ++i) fprintf(stderr, " %lld", h[((c * 5 + r) << 6) + i] ? h[((c * 5 + r) << 6) + i] - t0 : -1);
+      for (int i = 0; i < 40; ++i) fprintf(stderr, " %lld", h[((c * 8 + r) << 6) + i] ? h[((c * 8 + r) << 6) + i] - t0 : -1);
       fprintf(stderr, "\n");
     }
   }
@@ -697,10 +700,10 @@ static int launch(const float* A, int64_t lda, const float* Bt, int64_t ldb, con
   static int want_trace = -1;
   if (want_trace < 0) {
     want_trace = getenv("HRB_TC_TRACE") != nullptr ? 1 : 0;
-    if (want_trace) cudaMalloc((void**)&d_trace, 2 * 5 * 64 * sizeof(long long));
+    if (want_trace) cudaMalloc((void**)&d_trace, 2 * 8 * 64 * sizeof(long long));
   }
   g.trace = d_trace;
-  if (d_trace != nullptr) cudaMemsetAsync(d_trace, 0, 2 * 5 * 64 * sizeof(long long), st);
+  if (d_trace != nullptr) cudaMemsetAsync(d_trace, 0, 2 * 8 * 64 * sizeof(long long), st);
   static int a_tmem = -1;  // HRB_TC_A=smem keeps the A tile's hi/lo halves in shared memory (the first version of the kernel)
   if (a_tmem < 0) {
     const char* e = getenv("HRB_TC_A");

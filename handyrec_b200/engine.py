@@ -518,6 +518,7 @@ class DeepFMEngine:
         it = iter(batches)
         losses_host: List[torch.Tensor] = []
         sizes: List[int] = []
+        pool: List[torch.Tensor] = []  # pinned read-back slots are carved from 256-float chunks (one pinned allocation per 256 steps)
 
         def upload(slot, batch):
             ids_h, dense_h, label_h = batch
@@ -548,7 +549,10 @@ class DeepFMEngine:
             ids_d, dense_d, label_d = self._stage[cur_slot]
             self.train_step_on_device(ids_d[:B], dense_d[:B] if self.n_dense else None, label_d[:B])
             self._stage_free[cur_slot].record(main)
-            lh = torch.empty(1, dtype=torch.float32).pin_memory()
+            k = len(losses_host) % 256
+            if k == 0:
+                pool.append(torch.empty(256, dtype=torch.float32).pin_memory())
+            lh = pool[-1][k : k + 1]
             lh.copy_(self.loss_sum, non_blocking=True)  # D2H of this step's loss, not waited for here
             losses_host.append(lh)
             sizes.append(B)

@@ -1,0 +1,92 @@
+"""Turn ncu outputs into the markdown summaries committed under profiles/.
+
+  python profiles/summarize.py launches gpurun_out/launches.csv STEPS > profiles/rNN_launches.md
+      launches.csv = `ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file launches.csv python bench.py ...`
+      STEPS        = number of training steps the profiled command ran (warm-up + timed + e2e + per-phase profile step)
+  python profiles/summarize.py full gpurun_out/full_raw.csv > profiles/rNN_ncu_full.md
+      full_raw.csv = `ncu -i capture.ncu-rep --page raw --csv`
+"""
+import csv
+import io
+import re
+import sys
+from collections import OrderedDict
+
+
+def read_ncu_csv(path):
+    text = open(path, errors="replace").read()
+    start = text.find('"ID"')
+    if start < 0:
+        raise SystemExit(f"{path}: no ncu CSV header found")
+    return list(csv.DictReader(io.StringIO(text[start:])))
+
+
+def short(name):
+    name = re.sub(r"\(.*$", "", name)          # drop the argument list
+    name = name.replace("void ", "")
+    name = re.sub(r"cub::CUB_\d+_NS::", "cub::", name)
+    name = re.sub(r"cub::detail::\w+::", "cub::", name)
+    return name[:90]
+
+
+def launches(path, steps):
+    rows = read_ncu_csv(path)
+    agg = OrderedDict()
+    for r in rows:
+        if r.get("Metric Name") != "gpu__time_duration.sum":
+            continue
+        v = float(r["Metric Value"].replace(",", ""))
+        unit = r.get("Metric Unit", "ns")
+        us = v / 1e3 if unit.startswith("n") else (v if unit.startswith("u") else v * 1e3)
+        k = short(r["Kernel Name"])
+        a = agg.setdefault(k, [0, 0.0])
+        a[0] += 1
+        a[1] += us
+    total = sum(a[1] for a in agg.values())
+    print("| kernel | launches/step | avg µs | µs/step | share |")
+    print("|---|---:|---:|---:|---:|")
+    for k, (n, us) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+        print(f"| `{k}` | {n / steps:.1f} | {us / n:.1f} | {us / steps:.1f} | {100 * us / total:.1f}% |")
+    print(f"| **total** | {sum(a[0] for a in agg.values()) / steps:.1f} |  | {total / steps:.1f} | 100% |")
+
+
+FULL_METRICS = [
+    ("gpu__time_duration.sum", "duration"),
+    ("dram__bytes_read.sum", "dram read"),
+    ("dram__bytes_write.sum", "dram write"),
+    ("dram__throughput.avg.pct_of_peak_sustained_elapsed", "DRAM % of peak"),
+    ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "tensor-pipe active %"),
+    ("sm__inst_executed_pipe_uniform.sum", "uniform-pipe inst"),
+    ("sm__warps_active.avg.pct_of_peak_sustained_active", "warps active %"),
+    ("launch__registers_per_thread", "regs/thread"),
+    ("lts__t_sector_hit_rate.pct", "L2 hit %"),
+    ("l1tex__data_bank_conflicts_pipe_lsu.sum", "smem bank conflicts"),
+    ("smsp__cycles_active.avg", "SM active cycles"),
+]
+
+
+def full(path):
+    rows = read_ncu_csv(path)
+    # --page raw --csv: one row per launch, one column per metric (second line holds the units)
+    units = rows[0]
+    cols = [c for c in rows[0].keys()]
+    print("| kernel | " + " | ".join(label for _, label in FULL_METRICS) + " |")
+    print("|---|" + "---:|" * len(FULL_METRICS))
+    for r in rows[1:]:
+        cells = []
+        for m, _ in FULL_METRICS:
+            c = next((c for c in cols if c == m or c.startswith(m)), None)
+            if c is None or r.get(c, "") == "":
+                cells.append("–")
+                continue
+            cells.append(f"{r[c]} {units.get(c, '')}".strip())
+        print(f"| `{short(r.get('Kernel Name', '?'))}` | " + " | ".join(cells) + " |")
+
+
+if __name__ == "__main__":
+    if len(sys.argv) >= 4 and sys.argv[1] == "launches":
+        launches(sys.argv[2], float(sys.argv[3]))
+    elif len(sys.argv) >= 3 and sys.argv[1] == "full":
+        full(sys.argv[2])
+    else:
+        raise SystemExit(__doc__)

@@ -271,13 +271,18 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, tmem_base_smem, 0);
 
-  // work item -> (m tile, n tile, k split); n fastest so neighbouring CTAs share the A rows in L2
+  // work item -> (m tile, n tile, k split); n fastest so neighbouring CTAs share the A rows in L2.  The last n tile is NARROW
+  // (the MMA runs with N = its real width rounded to 16, e.g. 48 of 128 columns at N = 429), so tiles differ in cost: the n order
+  // inside a group is rotated by the pass number so that every CTA (stride w_step) meets all n tiles in turn.
   auto decode = [&](int64_t w, int& mt, int& nt, int& z) {
     z = (int)(w / ((int64_t)m_tiles * n_tiles));
     const int64_t r = w - (int64_t)z * m_tiles * n_tiles;
     mt = (int)(r / n_tiles);
     nt = (int)(r - (int64_t)mt * n_tiles);
+    nt = (int)((nt + ((int64_t)mt * n_tiles) / w_step) % n_tiles);
   };
+  // columns of n tile nt that exist, rounded up to the MMA's N granularity (16); this CTA's share of the B rows
+  auto n_width = [&](int nt) { return min(BN, (g.N - nt * BN + 15) & ~15); };
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -287,6 +292,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
         int mt, nt, z;
         decode(w, mt, nt, z);
         const int kb0 = z * g.kb_per_split, kb1 = min(kb_total, kb0 + g.kb_per_split);
+        const int b_half = PAIR ? n_width(nt) / 2 : 0;  // the pair splits the tile's REAL width: rank 1 starts at column n_width/2
         for (int kb = kb0; kb < kb1; ++kb, ++it) {
           const int s = it % STAGES;
           mbar_wait(&empty_bar[s], ((it / STAGES) & 1) ^ 1);
@@ -299,10 +305,10 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
           mbar_expect_tx(&full_bar[s], A_BYTES + B_BYTES);
           if (g.debug & 32) {
             tma_load_2d_cta(st, &map_a, &full_bar[s], kb * BK, mt * BMT + (int)pair_rank * BM);
-            tma_load_2d_cta(st + B_OFF, &map_b, &full_bar[s], kb * BK, nt * BN + (int)pair_rank * BNL);
+            tma_load_2d_cta(st + B_OFF, &map_b, &full_bar[s], kb * BK, nt * BN + (int)pair_rank * b_half);
           } else {
           tma_load_2d(st, &map_a, &full_bar[s], kb * BK, mt * BMT + (int)pair_rank * BM);
-          tma_load_2d(st + B_OFF, &map_b, &full_bar[s], kb * BK, nt * BN + (int)pair_rank * BNL);
+          tma_load_2d(st + B_OFF, &map_b, &full_bar[s], kb * BK, nt * BN + (int)pair_rank * b_half);
           }
         }
       }
@@ -315,11 +321,12 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
     if (leader) {
       // instruction descriptor (cute::UMMA::InstrDescriptor): c=F32 [4,6), a=b=TF32 [7,10)/[10,13),
       // K-major A and B (bits 15,16 = 0), N>>3 at [17,23), M>>4 at [24,29)
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BMT >> 4) << 24);
+      const uint32_t idesc0 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BMT >> 4) << 24);
       uint32_t it = 0, tcount = 0;
       for (int64_t w = w_first; w < n_work; w += w_step, ++tcount) {
         int mt, nt, z;
         decode(w, mt, nt, z);
+        const uint32_t idesc = idesc0 | ((uint32_t)(n_width(nt) >> 3) << 17);
         const int kb0 = z * g.kb_per_split, kb1 = min(kb_total, kb0 + g.kb_per_split);
         const int a = tcount & 1;
         if (PAIR)
@@ -473,8 +480,9 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
           v += __shfl_xor_sync(0xffffffffu, v, 1);
           v += __shfl_xor_sync(0xffffffffu, v, 2);
           v += __shfl_xor_sync(0xffffffffu, v, 4);
-          const int n = nt * BN + (int)pair_rank * BNL + (t >> 3) + 32 * j;
-          if (want_bsum && mt == 0 && (t & 7) == 0 && n < g.N) g.bsum[(size_t)z * g.N + n] = v;
+          const int b_half = PAIR ? n_width(nt) / 2 : BN, row = (t >> 3) + 32 * j;
+          const int n = nt * BN + (int)pair_rank * b_half + row;
+          if (want_bsum && mt == 0 && (t & 7) == 0 && row < b_half && n < g.N) g.bsum[(size_t)z * g.N + n] = v;
         }
       }
     }

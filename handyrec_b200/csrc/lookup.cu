@@ -429,30 +429,23 @@ __global__ void __launch_bounds__(256) lookup_rows_kernel(const FieldDev* __rest
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_addr_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-template <int G, bool FM>
+template <int G, bool FM, bool PEER>
 __global__ void __launch_bounds__(32 * G) lookup_tile_kernel(const FieldDev* __restrict__ fields_g, int32_t n_fields,
                                                             const int32_t* __restrict__ ids, int64_t ids_ld, int64_t batch,
                                                             float* __restrict__ out, int64_t out_ld, int32_t pitch /* floats */,
                                                             const float* __restrict__ fm_w, const float* __restrict__ fm_w0,
                                                             float* __restrict__ fm_out, float* __restrict__ fm_sum,
                                                             int32_t* __restrict__ oob, const float* const* __restrict__ peer_tab,
-                                                            const int64_t* __restrict__ full_rows, int32_t n_ranks, int32_t n_tables,
-                                                            int32_t gmode) {
+                                                            const int64_t* __restrict__ full_rows, int32_t n_ranks, int32_t n_tables) {
   constexpr int TS = 32;            // samples per tile
   constexpr int NT = 32 * G;        // threads: G lanes per sample
   constexpr int D = 4 * G;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float* tile = reinterpret_cast<float*>(smem_raw);                                   // [TS][pitch]
   FieldDev* fields = reinterpret_cast<FieldDev*>(smem_raw + (size_t)TS * pitch * 4);  // descriptors
-  __shared__ __align__(8) uint64_t gbar;
   for (int i = threadIdx.x; i < n_fields * (int)(sizeof(FieldDev) / 4); i += NT)
     reinterpret_cast<uint32_t*>(fields)[i] = reinterpret_cast<const uint32_t*>(fields_g)[i];
-  if (threadIdx.x == 0) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr_u32(&gbar)), "r"(NT));
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
   __syncthreads();
-  uint32_t gphase = 0;
   const int q = threadIdx.x % G, s = threadIdx.x / G;
   float4 w4 = make_float4(0.f, 0.f, 0.f, 0.f);
   float w0 = 0.f;
@@ -468,46 +461,11 @@ __global__ void __launch_bounds__(32 * G) lookup_tile_kernel(const FieldDev* __r
     const bool valid = b < batch;
     const int32_t* ids_row = ids + (valid ? b : 0) * ids_ld;
     float* my_row = tile + (size_t)s * pitch;
-    // gather: ids first (independent loads), then one 16-byte async copy per (field, chunk)
+    // gather: ids first (independent loads), then one 16-byte async copy per (field, chunk).  (A 64-byte 1-D bulk copy per row and a
+    // plain ld.global.nc + st.shared variant were measured too: within 2 % locally and over NVLink, so the simplest form stays.)
     constexpr int FU = 13;
-    if (gmode == 1) {
-      // experiment: one 1-D bulk copy (TMA) per row, lane q takes fields f == q (mod G)
-      uint32_t tx = 0;
-      for (int f = q; f < n_fields; f += G) {
-        const FieldDev& fd = fields[f];
-        const int32_t id = valid ? __ldg(ids_row + fd.ids_col) : -1;
-        float* dst = my_row + f * D;
-        const bool remote = peer_tab != nullptr && peer_tab[fd.table_idx] != nullptr;
-        const int64_t vocab = remote ? __ldg(full_rows + fd.table_idx) : fd.rows;
-        if (valid && id >= 0 && (int64_t)id < vocab) {
-          const float* src = remote ? peer_tab[(id % n_ranks) * n_tables + fd.table_idx] + (int64_t)(id / n_ranks) * D
-                                    : fd.table + (int64_t)id * D;
-          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr_u32(dst)),
-                       "l"(src), "r"((uint32_t)(D * 4)), "r"(smem_addr_u32(&gbar))
-                       : "memory");
-          tx += D * 4;
-        } else {
-#pragma unroll
-          for (int k = 0; k < G; ++k) reinterpret_cast<float4*>(dst)[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (valid && oob != nullptr) {
-            oob[0] = 1;
-            oob[1] = (int32_t)b;
-          }
-        }
-      }
-      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr_u32(&gbar)), "r"(tx) : "memory");
-      uint32_t done = 0;
-      while (!done)
-        asm volatile(
-            "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
-            : "=r"(done)
-            : "r"(smem_addr_u32(&gbar)), "r"(gphase)
-            : "memory");
-      gphase ^= 1;
-    } else {
     for (int f0 = 0; f0 < n_fields; f0 += FU) {
       int32_t id[FU];
-      float4 val[FU];
 #pragma unroll
       for (int u = 0; u < FU; ++u) id[u] = (valid && f0 + u < n_fields) ? __ldg(ids_row + fields[f0 + u].ids_col) : 0;
 #pragma unroll
@@ -516,7 +474,7 @@ __global__ void __launch_bounds__(32 * G) lookup_tile_kernel(const FieldDev* __r
           const FieldDev& f = fields[f0 + u];
           float* dst = my_row + (f0 + u) * D + q * 4;
           // a table without peer pointers is replicated: read the local copy
-          const bool remote = peer_tab != nullptr && peer_tab[f.table_idx] != nullptr;
+          const bool remote = PEER && peer_tab[f.table_idx] != nullptr;
           const int64_t vocab = remote ? __ldg(full_rows + f.table_idx) : f.rows;
           if (valid && id[u] >= 0 && (int64_t)id[u] < vocab) {
             const float* src;
@@ -524,13 +482,9 @@ __global__ void __launch_bounds__(32 * G) lookup_tile_kernel(const FieldDev* __r
               src = peer_tab[(id[u] % n_ranks) * n_tables + f.table_idx] + (int64_t)(id[u] / n_ranks) * D + q * 4;
             else
               src = f.table + (int64_t)id[u] * D + q * 4;
-            if (gmode == 2)
-              val[u] = ldg_nc_na(reinterpret_cast<const float4*>(src));
-            else
-              asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr_u32(dst)), "l"(src) : "memory");
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr_u32(dst)), "l"(src) : "memory");
           } else {
-            val[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (gmode != 2) *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+            *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
             if (valid && oob != nullptr) {
               oob[0] = 1;
               oob[1] = (int32_t)b;
@@ -538,15 +492,9 @@ __global__ void __launch_bounds__(32 * G) lookup_tile_kernel(const FieldDev* __r
           }
         }
       }
-      if (gmode == 2) {
-#pragma unroll
-        for (int u = 0; u < FU; ++u)
-          if (f0 + u < n_fields) *reinterpret_cast<float4*>(my_row + (f0 + u) * D + q * 4) = val[u];
-      }
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
     asm volatile("cp.async.wait_group 0;" ::: "memory");
-    }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // rows must be visible to the bulk-store engine
     __syncthreads();
     // one bulk store per sample row (1664 B at F=26, D=16): shared -> global, full lines
@@ -1290,29 +1238,27 @@ static int launch_rows(const hrb_plan* plan, const int32_t* ids, int64_t ids_ld,
       int64_t tiles = (batch + 31) / 32;
       int64_t grid = (int64_t)sm_count() * (per_sm < 1 ? 1 : (per_sm > 8 ? 8 : per_sm));
       if (grid > tiles) grid = tiles;
-      static int gmode = -1;
-      if (gmode < 0) {
-        const char* e = getenv("HRB_LOOKUP_GATHER");
-        gmode = e == nullptr ? 0 : (strcmp(e, "bulk") == 0 ? 1 : (strcmp(e, "ldg") == 0 ? 2 : 0));
-      }
-#define HRB_TILE(GG)                                                                                                          \
+#define HRB_TILE_P(GG, PP)                                                                                                    \
   {                                                                                                                           \
     static bool attr = false;                                                                                                 \
     if (!attr) {                                                                                                              \
-      HRB_CUDA(cudaFuncSetAttribute(lookup_tile_kernel<GG, FM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));    \
+      HRB_CUDA(cudaFuncSetAttribute(lookup_tile_kernel<GG, FM, PP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); \
       attr = true;                                                                                                            \
     }                                                                                                                         \
-    lookup_tile_kernel<GG, FM><<<(unsigned)grid, 32 * GG, smem, st>>>(plan->d_fields, plan->n_fields, ids, ids_ld, batch, out, \
-                                                                      out_ld, pitch, fm_w, fm_w0, fm_out, fm_sum, oob,        \
-                                                                      plan->d_peer_tab, plan->d_full_rows, plan->n_ranks,     \
-                                                                      plan->n_tables, gmode);                                 \
+    lookup_tile_kernel<GG, FM, PP><<<(unsigned)grid, 32 * GG, smem, st>>>(plan->d_fields, plan->n_fields, ids, ids_ld, batch, \
+                                                                          out, out_ld, pitch, fm_w, fm_w0, fm_out, fm_sum,    \
+                                                                          oob, plan->d_peer_tab, plan->d_full_rows,           \
+                                                                          plan->n_ranks, plan->n_tables);                     \
   }
+#define HRB_TILE(GG)                                                                                                          \
+  if (plan->d_peer_tab != nullptr) HRB_TILE_P(GG, true) else HRB_TILE_P(GG, false)
       switch (G) {
         case 2: HRB_TILE(2) break;
         case 4: HRB_TILE(4) break;
         case 8: HRB_TILE(8) break;
         default: HRB_TILE(16) break;
       }
+#undef HRB_TILE_P
 #undef HRB_TILE
       HRB_LAUNCH_CHECK();
       return HRB_OK;

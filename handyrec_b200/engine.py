@@ -128,7 +128,8 @@ class DeepFMEngine:
         self._segments.append((self.fm_off, off - self.fm_off, False))
         self.n_dense_params = off
         self._table_off = {}
-        for t in self.dense_tables:  # dense-updated tables live behind the dense parameters
+        for t in self.dense_tables:  # dense-updated tables live behind the dense parameters, rows on 128-byte lines like any table
+            off = (off + 31) // 32 * 32
             self._table_off[t] = off
             off += self.tables[t].numel()
         self.n_params = off

@@ -381,6 +381,8 @@ int hrb_tc_gemm_act_grad(const float* a, int64_t lda, const float* bt, int64_t l
 int hrb_tc_splits(int64_t M, int32_t N, int32_t K);
 int hrb_tc_gemm_splitk(const float* a, int64_t lda, const float* bt, int64_t ldb, int64_t M, int32_t N, int32_t K, int32_t splits,
                        float* part, int64_t ldp, float* bsum, cudaStream_t st);
+int hrb_tc_gemm_splitk_an(const float* x, int64_t ldx, const float* bt, int64_t ldb, int64_t M, int32_t N, int32_t K, int32_t splits,
+                          float* part, int64_t ldp, float* bsum, cudaStream_t st);
 int hrb_tc_dense_fwd(const float* x, int64_t ldx, const float* w, int64_t ldw, const float* bias, int64_t M, int32_t K,
                      int32_t N, int32_t act, float* y, int64_t ldy, cudaStream_t st);
 int hrb_tc_dense_bwd_x(const float* dz, int64_t lddz, const float* w, int64_t ldw, int64_t M, int32_t K, int32_t N,
@@ -545,6 +547,30 @@ HRB_API int hrb_dense_bwd_w_t(const float* xt, int64_t ldxt, const float* dzt, i
   // the bias gradient (column sums of dz = row sums of dz^T) rides along in the GEMM: its converter warps touch every element
   // of the dz^T tiles anyway and leave one partial sum per (split, column)
   int rc = hrb_tc_gemm_splitk(xt, ldxt, dzt, lddzt, K, N, (int32_t)M, splits, part, ldp, dbias != nullptr ? colpart : nullptr, st);
+  if (rc != HRB_OK) return rc;
+  launch_split_reduce(part, K, N, ldp, splits, dw, lddw, st);
+  HRB_LAUNCH_CHECK();
+  if (dbias != nullptr) {
+    launch_split_reduce(colpart, 1, N, N, splits, dbias, N, st);
+    HRB_LAUNCH_CHECK();
+  }
+  return HRB_OK;
+}
+
+// The same weight gradient from x AS STORED (x[M,K] row-major, no x^T copy): dw[K,N] = x^T * dz with dz given as dzt[N,M]
+HRB_API int hrb_dense_bwd_w_xn(const float* x, int64_t ldx, const float* dzt, int64_t lddzt, int64_t M, int32_t K, int32_t N, float* dw,
+                               int64_t lddw, float* dbias, void* workspace, size_t workspace_bytes, void* stream) {
+  HRB_REQUIRE(x && dzt && dw && workspace && M > 0 && K > 0 && N > 0 && ldx >= K && lddzt >= M && lddw >= N, "hrb_dense_bwd_w_xn: bad argument");
+  HRB_REQUIRE(M <= 0x7fffffff, "hrb_dense_bwd_w_xn: M too large");
+  size_t need = 0;
+  hrb_dense_bwd_w_t_workspace(M, K, N, &need);
+  if (workspace_bytes < need) return fail(HRB_WORKSPACE, "hrb_dense_bwd_w_xn: workspace %zu < required %zu bytes", workspace_bytes, need);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int splits = hrb_tc_splits(K, N, (int32_t)M);
+  const int64_t ldp = (N + 3) / 4 * 4;
+  float* part = (float*)workspace;
+  float* colpart = part + (size_t)splits * K * ldp;
+  int rc = hrb_tc_gemm_splitk_an(x, ldx, dzt, lddzt, K, N, (int32_t)M, splits, part, ldp, dbias != nullptr ? colpart : nullptr, st);
   if (rc != HRB_OK) return rc;
   launch_split_reduce(part, K, N, ldp, splits, dw, lddw, st);
   HRB_LAUNCH_CHECK();

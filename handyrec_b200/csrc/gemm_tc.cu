@@ -211,7 +211,10 @@ struct Args {
 #define HRB_TRACE(role, it_) \
   if (g.trace != nullptr && blockIdx.x < 2 && (it_) < 64) g.trace[((blockIdx.x * 8 + (role)) << 6) + (it_)] = clock64();
 
-template <int BN, int EPI, bool ATM, bool PAIR>
+// AMN (split-K weight gradient only): the A operand is given UNtransposed -- x[samples][features] as the forward stored it.  The
+// TMA box is 32 samples x 128 features (no swizzle, 512-byte rows) and the converter thread of feature row r picks x[k][r] for its 16
+// samples (consecutive lanes = consecutive words: conflict-free), so no x^T copy has to exist in HBM.
+template <int BN, int EPI, bool ATM, bool PAIR, bool AMN>
 __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a,
                                                              const __grid_constant__ CUtensorMap map_b,
                                                              const __grid_constant__ CUtensorMap map_c,
@@ -307,7 +310,10 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
             tma_load_2d_cta(st, &map_a, &full_bar[s], kb * BK, mt * BMT + (int)pair_rank * BM);
             tma_load_2d_cta(st + B_OFF, &map_b, &full_bar[s], kb * BK, nt * BN + (int)pair_rank * b_half);
           } else {
-          tma_load_2d(st, &map_a, &full_bar[s], kb * BK, mt * BMT + (int)pair_rank * BM);
+          if (AMN)
+            tma_load_2d(st, &map_a, &full_bar[s], mt * BMT + (int)pair_rank * BM, kb * BK);  // (feature, sample) coordinates
+          else
+            tma_load_2d(st, &map_a, &full_bar[s], kb * BK, mt * BMT + (int)pair_rank * BM);
           tma_load_2d(st + B_OFF, &map_b, &full_bar[s], kb * BK, nt * BN + (int)pair_rank * b_half);
           }
         }
@@ -413,7 +419,14 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
             uint32_t hi[16], lo[16];
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
-              const float4 x = src[(half * 4 + c) ^ (row & 7)];
+              float4 x;
+              if (AMN) {  // tile is [32 samples][128 features] plain: element (row, k) sits at k * 512 + row * 4 bytes
+                const float* col = reinterpret_cast<const float*>(st) + row;
+                x = make_float4(col[(half * 16 + c * 4 + 0) * 128], col[(half * 16 + c * 4 + 1) * 128], col[(half * 16 + c * 4 + 2) * 128],
+                                col[(half * 16 + c * 4 + 3) * 128]);
+              } else {
+                x = src[(half * 4 + c) ^ (row & 7)];
+              }
               const float xs[4] = {x.x, x.y, x.z, x.w};
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
@@ -695,7 +708,7 @@ static bool pair_enabled() {
   return v != 0;
 }
 
-template <int BN, int EPI>
+template <int BN, int EPI, bool AMN = false>
 static int launch(const float* A, int64_t lda, const float* Bt, int64_t ldb, const Args& g_in, cudaStream_t st) {
   Args g = g_in;
   static int dbg = -1;
@@ -719,7 +732,8 @@ static int launch(const float* A, int64_t lda, const float* Bt, int64_t ldb, con
   }
   const bool pair = a_tmem && pair_enabled();
   CUtensorMap ma, mb, mc, mct;
-  int rc = make_map2(&ma, A, g.M, g.K, lda, BK, BM, CU_TENSOR_MAP_SWIZZLE_128B);
+  int rc = AMN ? make_map2(&ma, A, g.K, g.M, lda, BM, BK, CU_TENSOR_MAP_SWIZZLE_NONE)  // A = x[K samples][M features], box 128 x 32
+               : make_map2(&ma, A, g.M, g.K, lda, BK, BM, CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc != HRB_OK) return rc;
   rc = make_map2(&mb, Bt, g.N, g.K, ldb, BK, pair ? BN / 2 : BN, CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc != HRB_OK) return rc;
@@ -737,9 +751,9 @@ static int launch(const float* A, int64_t lda, const float* Bt, int64_t ldb, con
   static_assert(smem_s <= 227 * 1024 && smem_t <= 227 * 1024, "shared memory budget");
   static bool attr_done = false;
   if (!attr_done) {
-    HRB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s));
-    HRB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t));
-    HRB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p));
+    HRB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI, false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s));
+    HRB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI, true, false, AMN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t));
+    HRB_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI, true, true, AMN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p));
     attr_done = true;
   }
   if (pair) {
@@ -758,7 +772,7 @@ static int launch(const float* A, int64_t lda, const float* Bt, int64_t ldb, con
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    HRB_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, EPI, true, true>, ma, mb, mc, mct, g));
+    HRB_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, EPI, true, true, AMN>, ma, mb, mc, mct, g));
     HRB_LAUNCH_CHECK();
     dump_trace(d_trace, st);
     return HRB_OK;
@@ -780,11 +794,11 @@ static int launch(const float* A, int64_t lda, const float* Bt, int64_t ldb, con
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    HRB_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, EPI, true, false>, ma, mb, mc, mct, g));
+    HRB_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, EPI, true, false, AMN>, ma, mb, mc, mct, g));
   } else if (a_tmem)
-    gemm_tc_kernel<BN, EPI, true, false><<<(unsigned)grid, THREADS, smem_t, st>>>(ma, mb, mc, mct, g);
+    gemm_tc_kernel<BN, EPI, true, false, AMN><<<(unsigned)grid, THREADS, smem_t, st>>>(ma, mb, mc, mct, g);
   else
-    gemm_tc_kernel<BN, EPI, false, false><<<(unsigned)grid, THREADS, smem_s, st>>>(ma, mb, mc, mct, g);
+    gemm_tc_kernel<BN, EPI, false, false, false><<<(unsigned)grid, THREADS, smem_s, st>>>(ma, mb, mc, mct, g);
   HRB_LAUNCH_CHECK();
   dump_trace(d_trace, st);
   return HRB_OK;
@@ -840,6 +854,18 @@ int hrb_tc_gemm_splitk(const float* a, int64_t lda, const float* bt, int64_t ldb
   if ((kb_total + per - 1) / per != splits) return fail(HRB_BAD_ARG, "tcgen05 split-K GEMM: %d splits leave empty slices", splits);
   tc::Args g{part, nullptr, nullptr, nullptr, ldp, 0, 0, M, N, K, 0, splits, per, nullptr, nullptr, 0, bsum, nullptr, 0};
   return tc::launch<128, tc::EPI_PLAIN>(a, lda, bt, ldb, g, st);
+}
+
+// same with the A operand untransposed: x[K samples][M features] row-major (the kernel transposes on its way into tensor memory)
+int hrb_tc_gemm_splitk_an(const float* x, int64_t ldx, const float* bt, int64_t ldb, int64_t M, int32_t N, int32_t K, int32_t splits,
+                          float* part, int64_t ldp, float* bsum, cudaStream_t st) {
+  if (!(aligned16(x) && aligned16(bt) && ldx % 4 == 0 && ldb % 4 == 0 && aligned16(part) && ldp % 4 == 0 && K >= 64))
+    return fail(HRB_UNSUPPORTED, "tcgen05 split-K GEMM: shape/alignment not covered");
+  const int kb_total = (K + tc::BK - 1) / tc::BK;
+  const int per = (kb_total + splits - 1) / splits;
+  if ((kb_total + per - 1) / per != splits) return fail(HRB_BAD_ARG, "tcgen05 split-K GEMM: %d splits leave empty slices", splits);
+  tc::Args g{part, nullptr, nullptr, nullptr, ldp, 0, 0, M, N, K, 0, splits, per, nullptr, nullptr, 0, bsum, nullptr, 0};
+  return tc::launch<128, tc::EPI_PLAIN, true>(x, ldx, bt, ldb, g, st);
 }
 
 // ---- hooks used by dense.cu (row-major weight layouts of hrb_dense_*) ---------------------------------------

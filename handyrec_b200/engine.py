@@ -174,13 +174,12 @@ class DeepFMEngine:
         self.fm_sum = torch.empty(B, self.D, **f32)
         self.prob = torch.empty(B, **f32)
         self.loss_sum = torch.zeros(1, **f32)
-        # tcgen05 path: transposed copies so that every GEMM operand has its reduction dim contiguous
+        # tcgen05 path: transposed copies (W^T, dZ^T) so that every GEMM operand has its reduction dim contiguous; the activations are
+        # read untransposed by the weight-gradient GEMM (hrb_dense_bwd_w_xn)
         self.use_tc = gemm_mode != _lib.GEMM_FP32 and B >= 512 and B % 4 == 0
         self.tc_layer = [self.use_tc and u >= 16 for u in self.units]
         if self.use_tc:
             self.Wt = [torch.zeros(ld, Kp, **f32) if tc else None for ld, Kp, tc in zip(self.layer_ld, self.layer_K, self.tc_layer)]
-            self.X0t = torch.zeros(self.K0p, B, **f32)
-            self.At = [torch.zeros(ld, B, **f32) for ld in self.layer_ld]
             self.dZt = [torch.zeros(ld, B, **f32) for ld in self.layer_ld]
             # relu sign bits of every hidden activation (1 bit/element) for the activation-gradient epilogue
             self.relu_mask = [torch.zeros(B, (u + 31) // 32, device=self.dev, dtype=torch.int32) if self.act == "relu" else None for u in self.units]
@@ -305,13 +304,11 @@ class DeepFMEngine:
                 call("hrb_dense1_fwd", K._p(x), ldx, K._p(self.W[i]), K._p(self.b[i]), B, self.layer_K[i], K._p(self.A[i]), st)
             elif self.use_tc and self.tc_layer[i] and B == self.B:
                 call("hrb_dense_fwd_t", K._p(x), ldx, K._p(self.Wt[i]), self.layer_K[i], K._p(self.b[i]), B, self.layer_K[i], self.units[i],
-                     _lib.ACT[act], K._p(self.A[i]), self.layer_ld[i], K._p(self.At[i]) if training else None, B,
+                     _lib.ACT[act], K._p(self.A[i]), self.layer_ld[i], None, B,
                      K._p(self.relu_mask[i]) if (training and act == "relu") else None, st)
             else:
                 call("hrb_dense_fwd", K._p(x), ldx, K._p(self.W[i]), self.layer_ld[i], K._p(self.b[i]), B, self.layer_K[i], self.units[i],
                      _lib.ACT[act], K._p(self.A[i]), self.layer_ld[i], _lib.GEMM_FP32, st)
-                if training and self.use_tc and B == self.B and i + 1 != n:  # a later tensor-core bwd_w reads A_i^T
-                    call("hrb_transpose", K._p(self.A[i]), B, self.units[i], self.layer_ld[i], K._p(self.At[i]), B, st)
             self._mark(f"dense_fwd_{i}")
             x, ldx = self.A[i], self.layer_ld[i]
         return self.A[-1]
@@ -366,9 +363,6 @@ class DeepFMEngine:
         need = ctypes.c_size_t(0)
         dz, lddz = self.dZ[-1], self.layer_ld[-1]
         tc_step = self.use_tc and B == self.B
-        if tc_step:
-            call("hrb_transpose", K._p(self.X0), B, self.K0p, self.K0p, K._p(self.X0t), B, st)
-            self._mark("transpose_x0")
         op = _lib.OptParams()
         op.opt = _lib.OPT_SGD if self.emb_opt == "sgd" else _lib.OPT_ADAM_LAZY
         op.lr, op.beta1, op.beta2, op.eps, op.l2_scale = self.lr, self.beta1, self.beta2, self.eps, 2.0 * self.l2_embd
@@ -417,15 +411,15 @@ class DeepFMEngine:
                 emb_part(side=True)
                 call("hrb_dense_bwd_w_t_workspace", B, Kp, N, ctypes.byref(need))
                 ws = self._dense_ws(need.value)
-                call("hrb_dense_bwd_w_t", K._p(self.X0t), B, K._p(self.dZt[0]), B, K._p(dz), lddz, B, Kp, N, K._p(self.dW[0]), self.layer_ld[0],
+                call("hrb_dense_bwd_w_xn", K._p(self.X0), self.K0p, K._p(self.dZt[0]), B, B, Kp, N, K._p(self.dW[0]), self.layer_ld[0],
                      K._p(self.db[0]), K._p(ws), ws.numel(), st)
                 self._mark("dense_bwd_w_0")
                 continue
             if tc_step and self.tc_layer[i]:
-                xt = self.At[i - 1] if i > 0 else self.X0t
                 call("hrb_dense_bwd_w_t_workspace", B, Kp, N, ctypes.byref(need))
                 ws = self._dense_ws(need.value)
-                call("hrb_dense_bwd_w_t", K._p(xt), B, K._p(self.dZt[i]), B, K._p(dz), lddz, B, Kp, N, K._p(self.dW[i]), self.layer_ld[i],
+                # x is read as the forward stored it: the GEMM transposes the tile on its way into tensor memory (no X0^T / A_i^T copies)
+                call("hrb_dense_bwd_w_xn", K._p(x), ldx, K._p(self.dZt[i]), B, B, Kp, N, K._p(self.dW[i]), self.layer_ld[i],
                      K._p(self.db[i]), K._p(ws), ws.numel(), st)
                 self._mark(f"dense_bwd_w_{i}")
                 if i > 0:

@@ -446,6 +446,25 @@ def dense_bwd_w_t(xt, dzt, dz=None, dw=None, dbias=None):
     return dw, dbias
 
 
+def dense_bwd_w_xn(x, dzt, dw=None, want_bias=True):
+    """dw (K, N) = x (M, K).T @ dz with dz given transposed (dzt (N, M)); x is read as stored, no x^T copy.  dbias = row sums of dzt."""
+    M, Kd = x.shape
+    N = dzt.shape[0]
+    need = ctypes.c_size_t(0)
+    call("hrb_dense_bwd_w_t_workspace", M, Kd, N, ctypes.byref(need))
+    key = ("t", x.device.index, torch.cuda.current_stream().cuda_stream)
+    ws = _dense_ws.get(key)
+    if ws is None or ws.numel() < need.value:
+        ws = torch.empty(need.value, device=x.device, dtype=torch.uint8)
+        _dense_ws[key] = ws
+    if dw is None:
+        dw = torch.empty(Kd, N, device=x.device, dtype=torch.float32)
+    dbias = torch.empty(N, device=x.device, dtype=torch.float32) if want_bias else None
+    call("hrb_dense_bwd_w_xn", _p(x), _row_major_2d(x, "x"), _p(dzt), _row_major_2d(dzt, "dzt"), M, Kd, N, _p(dw), _row_major_2d(dw, "dw"),
+         _p(dbias), _p(ws), ws.numel(), _stream())
+    return dw, dbias
+
+
 def dense1_fwd(x, w, bias, out=None):
     """The 1-unit logit layer: y (M,) = x (M,K) @ w (K,) + bias."""
     M, Kd = x.shape

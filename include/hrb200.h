@@ -207,6 +207,10 @@ int hrb_dense_bwd_w_t_workspace(int64_t M, int32_t K, int32_t N, size_t* bytes);
 int hrb_dense_bwd_w_t(const float* xt, int64_t ldxt, const float* dzt, int64_t lddzt, const float* dz, int64_t lddz, int64_t M,
                       int32_t K, int32_t N, float* dw, int64_t lddw, float* dbias, void* workspace, size_t workspace_bytes,
                       void* stream);
+/* The same weight gradient from x as the forward stored it (x[M,K] row-major): no x^T copy has to exist, the kernel
+ * transposes the tile on its way into tensor memory.  Workspace as hrb_dense_bwd_w_t_workspace. */
+int hrb_dense_bwd_w_xn(const float* x, int64_t ldx, const float* dzt, int64_t lddzt, int64_t M, int32_t K, int32_t N, float* dw,
+                       int64_t lddw, float* dbias, void* workspace, size_t workspace_bytes, void* stream);
 
 /* The 1-unit logit layer (models/ranking/context_aware/DeepFM.py:59-60): GEMV forward y[m] = x[m,:].w + b and a fused
  * backward dz_prev = dy (x) w * act'(x) (+ transposed copy), dw = x^T dy, dbias = sum dy (fixed-order reductions). */

@@ -76,6 +76,21 @@ def test_dense_bwd_w_t(dev, M, Kd, N):
     assert torch.equal(dw, k.dense_bwd_w_t(xt, dzt, dz.to(dev))[0])  # deterministic
 
 
+@pytest.mark.parametrize("M,Kd,N", [(65536, 432, 429), (4096, 256, 128), (2048, 132, 32), (1024, 40, 16)])
+def test_dense_bwd_w_untransposed_x(dev, M, Kd, N):
+    """The weight gradient from x as stored: the kernel transposes the tile on its way into tensor memory."""
+    k = K()
+    x = rnd(M, Kd, seed=3)
+    dz = rnd(M, N, seed=4)
+    want_w = (x.double().T @ dz.double()).float()
+    want_b = dz.double().sum(0).float()
+    dzt = k.transpose(dz.to(dev))
+    dw, db = k.dense_bwd_w_xn(x.to(dev), dzt)
+    close(dw, want_w, 1e-4)
+    close(db, want_b, 1e-4)
+    assert torch.equal(dw, k.dense_bwd_w_xn(x.to(dev), dzt)[0])  # deterministic
+
+
 def test_transpose_odd_shapes(dev):
     k = K()
     for r, c in ((1, 1), (33, 65), (1000, 13), (5, 432)):

@@ -329,9 +329,10 @@ def main():
     ach = gemm_flops / (gemm_ms * 1e-3) / 1e12
     roofline = {"kernel": "tc::gemm_tc_kernel (tcgen05 3xTF32, %d launches/step; bwd_w phases include their split-reduce/colsum kernels)" % len(gemm_names),
                 "bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": ach / peaks["bf16_tflops_sustained"],
-                "traffic": None, "share_of_step": gemm_ms / total_phase, "flops_per_step": gemm_flops,
+                "traffic": 182.1e6 if B == BATCH else None, "traffic_note": "dram read+write per launch, mean of the step's 9 GEMM launches in profiles/r01_ncu_full_summary.md (1639 MB per step, captured before the transposed activation stores were dropped)",
+                "share_of_step": gemm_ms / total_phase, "flops_per_step": gemm_flops,
                 "peak_source": f"{peaks['source']} bf16 sustained (kernel timed inside a long step)",
-                "note": "fp32 parity needs 3 TF32 MMAs per product at half the bf16 rate: ceiling of this scheme = 1/6 = 0.167 of the bf16 peak (DESIGN.md 3); ncu tensor-pipe active 34-48% (profiles/r01_ncu_full_summary.md)"}
+                "note": "fp32 parity needs 3 TF32 MMAs per product at half the bf16 rate: ceiling of this scheme = 1/6 = 0.167 of the bf16 peak (DESIGN.md 3); ncu tensor-pipe active 58-80% on the large GEMMs (profiles/r01_ncu_full_summary.md)"}
     lk = "lookup_fm_fwd" if (world == 1 or eng.peer_lookup) else "sharded_lookup_fwd"
     lk_ach = lookup_bytes / (phases[lk] * 1e-3) / 1e9
     peer = world > 1 and eng.peer_lookup
@@ -340,7 +341,7 @@ def main():
     rl_lookup = {"kernel": "hrb::lookup_tile_kernel (fused lookup + FM)" if world == 1 else
                  ("hrb::lookup_tile_kernel reading row-sharded tables over NVLink peer mappings" if peer else "row exchange (route + all-to-all + gather + scatter)"),
                  "bound": "hbm", "achieved": lk_ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": lk_ach / peaks["hbm_gbs"],
-                 "traffic": 159.0e6 if world == 1 else None, "nvlink_bytes_per_step": None if world == 1 else B * n_sharded * EMB_DIM * 4 * (world - 1) / world, "traffic_note": "dram read+write per launch from profiles/r01_ncu_full_summary.md",
+                 "traffic": 163.7e6 if (world == 1 and B == BATCH) else None, "nvlink_bytes_per_step": None if world == 1 else B * n_sharded * EMB_DIM * 4 * (world - 1) / world, "traffic_note": "dram read+write per launch from profiles/r01_ncu_full_summary.md",
                  "peak_source": f"{peaks['source']} copy bandwidth", "bytes_per_sample": LOOKUP_BYTES_PER_SAMPLE, "in_step_ms": phases[lk],
                  "alone_ms": lookup_alone_ms, "alone_achieved": lookup_bytes / (lookup_alone_ms * 1e-3) / 1e9,
                  "alone_frac": lookup_bytes / (lookup_alone_ms * 1e-3) / 1e9 / peaks["hbm_gbs"]}

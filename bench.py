@@ -136,6 +136,9 @@ def cpu_reference_arm(batch: int, vocab_cap: int, steps: int, warmup: int, seed:
             "sample": f"{steps} steps of batch {batch}, vocab capped at {vocab_cap} rows/table, Adam, torch-CPU op-for-op restatement (TF unavailable in image)"}
 
 
+WORKLOAD = "DeepFM Criteo-shape: 26 sparse + 13 dense, emb dim 16, DNN 429-256-128-1, batch 65536/GPU (BASELINE.json configs[2])"
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -145,7 +148,8 @@ def run_reference(args):
         "impl": "reference", "metric": "DeepFM train samples/s", "value": r["samples_per_s"], "unit": "samples/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "DeepFM Criteo-shape (26 sparse + 13 dense, D=16, DNN 429-256-128-1), CPU restatement of the reference", "global_batch": 8192},
+        "config": {"workload": WORKLOAD, "global_batch": 8192,
+                   "reference_sample": "CPU restatement of the reference (oracle/) on a bounded sample of the workload: " + r["sample"]},
         "cpu_baseline": {"value": r["samples_per_s"], "unit": "samples/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]},
         "e2e": {"value": r["samples_per_s"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -363,7 +367,7 @@ def main():
         "metric": "DeepFM train samples/s", "value": B * world * args.steps / (ms * 1e-3), "unit": "samples/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "DeepFM Criteo-shape: 26 sparse + 13 dense, emb dim 16, DNN 429-256-128-1, batch 65536/GPU (BASELINE.json configs[2])",
+        "config": {"workload": WORKLOAD,
                    "global_batch": B * world, "tables_rows": sum(vocabs), "tables_gb": sum(vocabs) * EMB_DIM * 4 / 1e9, "ids": args.ids,
                    "optimizer": f"{args.optimizer} (dense params and the {n_small} tables of <= {args.small_table_rows} rows, Keras-exact dense step) + {eng.emb_opt} (touched rows of the {n_sharded} large tables)", "l2_embd": 0.0,
                    "l2_flush": "inputs larger than L2 (6.5 GB of tables, rotating pool of 4 batches)", "scale_vocab": args.scale_vocab,

@@ -46,6 +46,37 @@ def build():
     return arrays
 
 
+def build_din():
+    """DIN local-activation attention at the ml-1m-test DIN shape in miniature (layers/sequence.py:92-102 + tools.py:104-113 +
+    models/ranking/sequential/DIN.py:87-93): B=6 users, history length T=5 (one user with an all-padding history, one full),
+    D=8, LAU tower (16, 8, 1) with Dice and with relu."""
+    D, B, T, V = 8, 6, 5, 40
+    table = torch.from_numpy(oracle.hash_uniform_table(V, D, seed=300, lo=-0.5, hi=0.5))
+    qid = np.array([[3], [7], [1], [39], [12], [5]], dtype=np.int32)
+    kid = np.array([[4, 9, 0, 0, 0], [0, 0, 0, 0, 0], [1, 2, 3, 4, 5], [39, 39, 0, 0, 0], [8, 0, 0, 0, 0], [5, 6, 7, 0, 0]], dtype=np.int32)
+    out = {"din_table": table.numpy(), "din_qid": qid, "din_kid": kid}
+    for act in ("dice", "relu"):
+        p = oracle.dnn_init(4 * D, (16, 8, 1), seed=11)
+        for i, u in enumerate(p.units):
+            p.b[i] = torch.from_numpy(oracle.hash_uniform_table(1, u, seed=400 + i, lo=-0.1, hi=0.1))[0]
+            p.dice_alpha[i] = torch.from_numpy(oracle.hash_uniform_table(1, u, seed=410 + i, lo=-0.3, hi=0.3))[0]
+            p.dice_mean[i] = torch.from_numpy(oracle.hash_uniform_table(1, u, seed=420 + i, lo=-0.1, hi=0.1))[0]
+            p.dice_var[i] = torch.from_numpy(oracle.hash_uniform_table(1, u, seed=430 + i, lo=0.5, hi=1.5))[0]
+        q, _ = oracle.custom_embedding(table, torch.from_numpy(qid), True)
+        keys, kmask = oracle.custom_embedding(table, torch.from_numpy(kid), True)
+        keys, kmask = oracle.squeeze_mask(keys, kmask)
+        score = oracle.local_activation_unit(q, keys, kmask, p, act=act, training=False)
+        out[f"din_score_{act}"] = score.numpy()
+        out[f"din_pooled_{act}"] = oracle.din_attention_pool(score, keys).numpy()
+        if act == "dice":
+            for i in range(len(p.units)):
+                out[f"din_W{i}"], out[f"din_b{i}"] = p.W[i].numpy(), p.b[i].numpy()
+                out[f"din_alpha{i}"], out[f"din_mean{i}"], out[f"din_var{i}"] = p.dice_alpha[i].numpy(), p.dice_mean[i].numpy(), p.dice_var[i].numpy()
+    return out
+
+
 if __name__ == "__main__":
-    np.savez_compressed(os.path.join(os.path.dirname(__file__), "c1_deepfm.npz"), **build())
-    print("wrote c1_deepfm.npz")
+    here = os.path.dirname(__file__)
+    np.savez_compressed(os.path.join(here, "c1_deepfm.npz"), **build())
+    np.savez_compressed(os.path.join(here, "c2_din.npz"), **build_din())
+    print("wrote c1_deepfm.npz, c2_din.npz")

@@ -51,3 +51,46 @@ def test_cuda_matches_golden(dev):
     prob = eng.predict_on_device(ids, torch.from_numpy(gold["x_year"]).to(dev)).cpu().numpy()
     np.testing.assert_allclose(prob, gold["prob"][:, 0], rtol=1e-5, atol=1e-7)
     np.testing.assert_allclose(eng.fm_out.cpu().numpy(), gold["fm"][:, 0], rtol=1e-5, atol=1e-6)
+
+
+GOLD_DIN = os.path.join(HERE, "golden", "c2_din.npz")
+
+
+def test_oracle_reproduces_din_golden():
+    import make_golden
+
+    gold = np.load(GOLD_DIN)
+    now = make_golden.build_din()
+    assert set(now) == set(gold.files)
+    for k in gold.files:
+        np.testing.assert_array_equal(now[k], gold[k], err_msg=k)
+    # hand-checkable: padded positions score exactly 0 (att_out * mask, layers/sequence.py:101); the user with an all-padding
+    # history pools to the zero vector (tf.matmul(att, keys), DIN.py:93); there is no softmax, so scores need not sum to 1
+    for act in ("dice", "relu"):
+        s, pooled = gold[f"din_score_{act}"], gold[f"din_pooled_{act}"]
+        assert s.shape == (6, 1, 5) and pooled.shape == (6, 1, 8)
+        assert np.all(s[:, 0][gold["din_kid"] == 0] == 0) and np.all(pooled[1] == 0)
+        assert np.all(s[2, 0] != 0)
+        # identical history items get identical scores (row 3: movie 39 twice)
+        assert s[3, 0, 0] == s[3, 0, 1]
+
+
+@pytest.mark.gpu
+def test_cuda_matches_din_golden(dev):
+    from handyrec_b200 import kernels as K
+
+    gold = np.load(GOLD_DIN)
+    table = torch.from_numpy(gold["din_table"]).to(dev)
+    qid = torch.from_numpy(gold["din_qid"]).reshape(-1).to(dev)
+    kid = torch.from_numpy(gold["din_kid"]).to(dev)
+    W = [torch.from_numpy(gold[f"din_W{i}"]).to(dev) for i in range(4)]
+    b = [torch.from_numpy(gold[f"din_b{i}"]).to(dev) for i in range(4)]
+    dice = [tuple(torch.from_numpy(gold[f"din_{n}{i}"]).to(dev) for n in ("alpha", "mean", "var")) for i in range(4)]
+    units = [w.shape[1] for w in W]
+    for act in ("dice", "relu"):
+        params = K.lau_pack_params(W, b, dice if act == "dice" else None)
+        score, pooled = K.lau_fwd(table, qid, kid, params, units, act)
+        got_s, got_p = score.cpu().numpy(), pooled.cpu().numpy()
+        assert np.all(got_s[:, 0][gold["din_kid"] == 0] == 0)  # the mask is exact
+        np.testing.assert_allclose(got_s, gold[f"din_score_{act}"], rtol=1e-5, atol=1e-7)
+        np.testing.assert_allclose(got_p, gold[f"din_pooled_{act}"], rtol=1e-5, atol=1e-7)

@@ -71,12 +71,6 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, u
       "l"(map), "r"(s32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
-__device__ __forceinline__ void tma_load_2d_cta(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(s32(dst)),
-      "l"(map), "r"(s32(bar)), "r"(c0), "r"(c1)
-      : "memory");
-}
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* src, int c0, int c1, int c2) {
   asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(map), "r"(s32(src)), "r"(c0),
                "r"(c1), "r"(c2)
@@ -306,16 +300,11 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
           }
           HRB_TRACE(0, it)
           mbar_expect_tx(&full_bar[s], A_BYTES + B_BYTES);
-          if (g.debug & 32) {
-            tma_load_2d_cta(st, &map_a, &full_bar[s], kb * BK, mt * BMT + (int)pair_rank * BM);
-            tma_load_2d_cta(st + B_OFF, &map_b, &full_bar[s], kb * BK, nt * BN + (int)pair_rank * b_half);
-          } else {
           if (AMN)
             tma_load_2d(st, &map_a, &full_bar[s], mt * BMT + (int)pair_rank * BM, kb * BK);  // (feature, sample) coordinates
           else
             tma_load_2d(st, &map_a, &full_bar[s], kb * BK, mt * BMT + (int)pair_rank * BM);
           tma_load_2d(st + B_OFF, &map_b, &full_bar[s], kb * BK, nt * BN + (int)pair_rank * b_half);
-          }
         }
       }
     }
@@ -725,11 +714,13 @@ static int launch(const float* A, int64_t lda, const float* Bt, int64_t ldb, con
   }
   g.trace = d_trace;
   if (d_trace != nullptr) cudaMemsetAsync(d_trace, 0, 2 * 8 * 64 * sizeof(long long), st);
-  static int a_tmem = -1;  // HRB_TC_A=smem keeps the A tile's hi/lo halves in shared memory (the first version of the kernel)
+  // HRB_TC_A=smem keeps the A tile's hi/lo halves in shared memory (the first version of the kernel; not for the untransposed-A form)
+  static int a_tmem = -1;
   if (a_tmem < 0) {
     const char* e = getenv("HRB_TC_A");
     a_tmem = (e != nullptr && strcmp(e, "smem") == 0) ? 0 : 1;
   }
+  if (AMN && !a_tmem) return fail(HRB_UNSUPPORTED, "tcgen05 GEMM: the untransposed-A weight gradient needs A in tensor memory (unset HRB_TC_A)");
   const bool pair = a_tmem && pair_enabled();
   CUtensorMap ma, mb, mc, mct;
   int rc = AMN ? make_map2(&ma, A, g.K, g.M, lda, BM, BK, CU_TENSOR_MAP_SWIZZLE_NONE)  // A = x[K samples][M features], box 128 x 32
@@ -779,23 +770,7 @@ static int launch(const float* A, int64_t lda, const float* Bt, int64_t ldb, con
   }
   const int64_t work = (int64_t)((g.M + BM - 1) / BM) * ((g.N + BN - 1) / BN) * g.splits;
   int64_t grid = work < sm_count() ? work : sm_count();
-  static int cl1 = -1;
-  if (cl1 < 0) cl1 = getenv("HRB_TC_CLUSTER1") != nullptr ? 1 : 0;
-  if (a_tmem && cl1) {  // experiment: the single-CTA kernel launched as clusters of 2 (no functional change)
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)(grid & ~1ll));
-    cfg.blockDim = dim3(THREADS);
-    cfg.dynamicSmemBytes = smem_t;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    HRB_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, EPI, true, false, AMN>, ma, mb, mc, mct, g));
-  } else if (a_tmem)
+  if (a_tmem)
     gemm_tc_kernel<BN, EPI, true, false, AMN><<<(unsigned)grid, THREADS, smem_t, st>>>(ma, mb, mc, mct, g);
   else
     gemm_tc_kernel<BN, EPI, false, false, false><<<(unsigned)grid, THREADS, smem_s, st>>>(ma, mb, mc, mct, g);

@@ -297,6 +297,64 @@ __global__ void __launch_bounds__(256) dense1_bwd_dz_kernel(const float* __restr
 }
 
 // part[blockIdx.y][k] = sum over the row slab of x[m,k]*dy[m]; part[blockIdx.y][K] = sum dy  (32 columns x 8 row lanes)
+// The logit layer's backward in one pass over x: a CTA walks 32-row tiles, writes dz, stages x and dz in shared memory, writes the
+// transposed dz tile (128-byte rows of dz^T) and keeps its dw / dbias partial sums in registers across tiles (fixed tile and row
+// order -> deterministic).  Shared memory: 2 x 32 x (K+1) floats, so K <= 190; wider layers take the three-kernel path.
+constexpr int D1_ROWS = 32;
+__global__ void __launch_bounds__(256) dense1_bwd_fused_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ w,
+                                                              const float* __restrict__ dy, int64_t M, int32_t K, int32_t act,
+                                                              float* __restrict__ dzp, int64_t lddz, float* __restrict__ dzt, int64_t lddzt,
+                                                              float* __restrict__ part) {
+  extern __shared__ float d1_smem[];
+  const int P = K + 1, K4 = K >> 2;
+  float* xs = d1_smem;
+  float* zs = xs + D1_ROWS * P;
+  float* dys = zs + D1_ROWS * P;
+  const int64_t n_tiles = (M + D1_ROWS - 1) / D1_ROWS;
+  float acc = 0.f, accb = 0.f;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int64_t m0 = tile * D1_ROWS;
+    if (threadIdx.x < D1_ROWS) dys[threadIdx.x] = (m0 + threadIdx.x < M) ? __ldg(dy + m0 + threadIdx.x) : 0.f;
+    __syncthreads();
+    for (int i = threadIdx.x; i < D1_ROWS * K4; i += 256) {
+      const int r = i / K4, c = i - r * K4;
+      const int64_t m = m0 + r;
+      float4 xv = make_float4(0.f, 0.f, 0.f, 0.f), o = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (m < M) {
+        xv = __ldg(reinterpret_cast<const float4*>(x + m * ldx) + c);
+        const float4 wv = __ldg(reinterpret_cast<const float4*>(w) + c);
+        const float g = dys[r];
+        o.x = g * wv.x * act_grad_from_out(act, xv.x);
+        o.y = g * wv.y * act_grad_from_out(act, xv.y);
+        o.z = g * wv.z * act_grad_from_out(act, xv.z);
+        o.w = g * wv.w * act_grad_from_out(act, xv.w);
+        reinterpret_cast<float4*>(dzp + m * lddz)[c] = o;
+      }
+      float* xr = xs + r * P + 4 * c;
+      float* zr = zs + r * P + 4 * c;
+      xr[0] = xv.x; xr[1] = xv.y; xr[2] = xv.z; xr[3] = xv.w;
+      zr[0] = o.x; zr[1] = o.y; zr[2] = o.z; zr[3] = o.w;
+    }
+    __syncthreads();
+    if (dzt != nullptr) {
+      for (int i = threadIdx.x; i < K * D1_ROWS; i += 256) {
+        const int k = i / D1_ROWS, r = i - k * D1_ROWS;
+        if (m0 + r < M) dzt[(int64_t)k * lddzt + m0 + r] = zs[r * P + k];
+      }
+    }
+    if ((int)threadIdx.x < K) {
+#pragma unroll 8
+      for (int r = 0; r < D1_ROWS; ++r) acc = fmaf(xs[r * P + threadIdx.x], dys[r], acc);
+    }
+    if (threadIdx.x == 255) {
+#pragma unroll 8
+      for (int r = 0; r < D1_ROWS; ++r) accb += dys[r];
+    }
+    __syncthreads();  // the next tile overwrites dys / xs / zs
+  }
+  if ((int)threadIdx.x < K) part[(int64_t)blockIdx.x * (K + 1) + threadIdx.x] = acc;
+  if (threadIdx.x == 255) part[(int64_t)blockIdx.x * (K + 1) + K] = accb;
+}
 __global__ void __launch_bounds__(256) dense1_bwd_dw_kernel(const float* __restrict__ x, int64_t ldx, const float* __restrict__ dy,
                                                            int64_t M, int32_t K, int64_t rows_per_block, float* __restrict__ part) {
   const int k = blockIdx.x * 32 + (threadIdx.x & 31);
@@ -613,6 +671,21 @@ HRB_API int hrb_dense1_bwd(const float* x, int64_t ldx, const float* w, const fl
   hrb_dense1_bwd_workspace(M, K, &need);
   if (workspace_bytes < need) return fail(HRB_WORKSPACE, "hrb_dense1_bwd: workspace %zu < required %zu bytes", workspace_bytes, need);
   cudaStream_t st = (cudaStream_t)stream;
+  const size_t fused_smem = ((size_t)2 * D1_ROWS * (K + 1) + D1_ROWS) * sizeof(float);
+  if (K <= 190 && fused_smem <= 48 * 1024) {  // one pass: dz, dz^T and the dw / dbias partials of every CTA
+    const int64_t tiles = (M + D1_ROWS - 1) / D1_ROWS;
+    const int grid = (int)min((int64_t)min(512, sm_count() * 3), tiles);
+    float* part = (float*)workspace;
+    dense1_bwd_fused_kernel<<<grid, 256, fused_smem, st>>>(x, ldx, w, dy, M, K, act_prev, dz_prev, lddz, dz_prev_t, lddzt, part);
+    HRB_LAUNCH_CHECK();
+    launch_split_reduce(part, 1, K, K + 1, grid, dw, K, st);
+    HRB_LAUNCH_CHECK();
+    if (dbias != nullptr) {
+      launch_split_reduce(part + K, 1, 1, K + 1, grid, dbias, 1, st);
+      HRB_LAUNCH_CHECK();
+    }
+    return HRB_OK;
+  }
   const int64_t total = M * (K / 4);
   const int64_t blocks = min((int64_t)sm_count() * 8, (total + 255) / 256);
   dense1_bwd_dz_kernel<<<(unsigned)blocks, 256, 0, st>>>(x, ldx, w, dy, M, K / 4, act_prev, dz_prev, lddz);

@@ -98,7 +98,7 @@ def test_transpose_odd_shapes(dev):
         assert torch.equal(k.transpose(x.to(dev)).cpu(), x.t().contiguous())
 
 
-@pytest.mark.parametrize("M,Kd,act", [(65536, 128, "relu"), (1000, 36, "sigmoid"), (33, 8, None), (4096, 132, "relu")])
+@pytest.mark.parametrize("M,Kd,act", [(65536, 128, "relu"), (1000, 36, "sigmoid"), (33, 8, None), (4096, 132, "relu"), (2050, 256, "relu"), (777, 188, None)])
 def test_dense1_logit_layer(dev, M, Kd, act):
     k = K()
     ld = (Kd + 3) // 4 * 4

@@ -22,6 +22,7 @@ POOL = {"none": 0, None: 0, "mean": 1, "sum": 2, "max": 3}
 ACT = {None: 0, "linear": 0, "relu": 1, "sigmoid": 2, "tanh": 3, "dice": 4}
 OPT_SGD, OPT_ADAM_LAZY = 0, 1
 GEMM_AUTO, GEMM_FP32, GEMM_3XTF32 = 0, 1, 2
+BWD_AUTO, BWD_UNITS, BWD_SORT = 0, 1, 2
 
 
 class HrbError(RuntimeError):

@@ -239,6 +239,28 @@ class SigmoidBCEFn(torch.autograd.Function):
         return (dl * g).reshape(-1, 1), None
 
 
+class ClippedBCEFn(torch.autograd.Function):
+    """mean binary cross-entropy on probabilities clipped to [1e-7, 1-1e-7] (Keras' path without cached logits)."""
+
+    @staticmethod
+    def forward(ctx, prob, label):
+        shape = prob.shape
+        prob = prob.contiguous().reshape(-1)
+        label = label.contiguous().reshape(-1).to(torch.float32)
+        n = prob.numel()
+        dp = torch.empty_like(prob)
+        ls = torch.zeros(1, device=prob.device, dtype=torch.float32)
+        call("hrb_clipped_bce", K._p(prob), K._p(label), n, 1e-7, 1.0 / n, K._p(dp), K._p(ls), K._stream())
+        ctx.save_for_backward(dp)
+        ctx.shape = shape
+        return (ls / n).reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        (dp,) = ctx.saved_tensors
+        return (dp * g).reshape(ctx.shape), None
+
+
 class ActivationFn(torch.autograd.Function):
     """Stand-alone Keras Activation(name) for relu / sigmoid / tanh (element-wise)."""
 

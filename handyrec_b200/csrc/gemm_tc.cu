@@ -202,8 +202,16 @@ struct Args {
 // MMA thread issues for both, tcgen05.commit multicasts the "stage free" / "accumulator full" arrivals to both CTAs, the peer's
 // converter and epilogue warps arrive on the leader's barriers through the cluster address space.  Per CTA and k-block this moves
 // 24 KB instead of 32 KB from L2 and 80 KB instead of 128 KB through shared memory.
+// Perf-debugging hooks (ablation bits, clock64 stamps, alternative variants selected by HRB_TC_* environment variables) exist
+// only in a -DHRB_DEVTOOLS build; the shipped library has none of them.
+#ifdef HRB_DEVTOOLS
+#define HRB_DBG(b) (g.debug & (b))
 #define HRB_TRACE(role, it_) \
   if (g.trace != nullptr && blockIdx.x < 2 && (it_) < 64) g.trace[((blockIdx.x * 8 + (role)) << 6) + (it_)] = clock64();
+#else
+#define HRB_DBG(b) 0
+#define HRB_TRACE(role, it_)
+#endif
 
 // AMN (split-K weight gradient only): the A operand is given UNtransposed -- x[samples][features] as the forward stored it.  The
 // TMA box is 32 samples x 128 features (no swizzle, 512-byte rows) and the converter thread of feature row r picks x[k][r] for its 16
@@ -294,7 +302,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
           const int s = it % STAGES;
           mbar_wait(&empty_bar[s], ((it / STAGES) & 1) ^ 1);
           unsigned char* st = tiles + (size_t)s * STAGE_BYTES;
-          if (g.debug & 8) {
+          if (HRB_DBG(8)) {
             mbar_arrive(&full_bar[s]);
             continue;
           }
@@ -345,7 +353,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
             HRB_TRACE(3, it)
             if (ATM) {
               const uint32_t ta_hi = tmem_base + ACC_COLS + (uint32_t)s * A_COLS, ta_lo = ta_hi + BK;
-              if (!(g.debug & 4))
+              if (!(HRB_DBG(4)))
 #pragma unroll
               for (int kk = 0; kk < BK / 8; ++kk) {  // UMMA_K = 8 tf32: 8 TMEM columns of A, 32 bytes of B
                 const uint64_t o = (uint64_t)(kk * 2);
@@ -361,7 +369,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
               }
             } else {
               const uint64_t a_hi = make_desc(st), a_lo = make_desc(st + A_BYTES);
-              if (!(g.debug & 4))
+              if (!(HRB_DBG(4)))
 #pragma unroll
               for (int kk = 0; kk < BK / 8; ++kk) {  // UMMA_K = 8 tf32 = 32 bytes: +2 in the (>>4) start-address field
                 const uint64_t o = (uint64_t)(kk * 2);
@@ -401,7 +409,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
         if (ATM) {
           // A: this thread owns row (warp%4)*32+lane of the tile (the TMEM lanes its warp may touch) and 16 of the 32 k-columns;
           // row r of a SWIZZLE_128B tile keeps its 16-byte chunk c at chunk c ^ (r % 8)
-          if (!(g.debug & 2)) {
+          if (!(HRB_DBG(2))) {
             const int qrow = warp & 3, half = (warp - CONV_WARP0) >> 2;
             const int row = qrow * 32 + lane;
             const float4* src = reinterpret_cast<const float4*>(st + row * 128);
@@ -431,7 +439,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
           }
         } else {
         // element-wise, so the swizzled placement is irrelevant: lo lands at the same offset as hi
-        if (!(g.debug & 2))
+        if (!(HRB_DBG(2)))
 #pragma unroll 4
         for (int i = t; i < (int)(A_BYTES / 16); i += CONV_THREADS) {
           float4* p = reinterpret_cast<float4*>(st) + i;
@@ -440,11 +448,11 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
           h.y = __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u);
           h.z = __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u);
           h.w = __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u);
-          if (g.debug & 16) *p = h;  // the MMA reads only the TF32 bits of the raw fp32 operand: writing hi back is redundant
+          if (HRB_DBG(16)) *p = h;  // the MMA reads only the TF32 bits of the raw fp32 operand: writing hi back is redundant
           reinterpret_cast<float4*>(st + A_BYTES)[i] = make_float4(x.x - h.x, x.y - h.y, x.z - h.z, x.w - h.w);
         }
         }
-        if (!(g.debug & 2))
+        if (!(HRB_DBG(2)))
 #pragma unroll
         for (int j = 0; j < B_PER_THREAD; ++j) {
           const int i = t + j * CONV_THREADS;
@@ -454,7 +462,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
           h.y = __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u);
           h.z = __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u);
           h.w = __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u);
-          if (g.debug & 16) *p = h;  // the MMA reads only the TF32 bits of the raw fp32 operand: writing hi back is redundant
+          if (HRB_DBG(16)) *p = h;  // the MMA reads only the TF32 bits of the raw fp32 operand: writing hi back is redundant
           reinterpret_cast<float4*>(st + B_OFF + B_BYTES)[i] = make_float4(x.x - h.x, x.y - h.y, x.z - h.z, x.w - h.w);
           if (EPI == EPI_PLAIN) bs[j] += (x.x + x.y) + (x.z + x.w);  // row sums of Bt ride along (bias gradient)
         }
@@ -467,7 +475,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
             HRB_TRACE(3, it)
             // relaxed: the writes were fenced to the async proxy by every thread and ordered by the bar.sync above; a
             // release at cluster scope stalls this thread for 1000-2000 cycles per k-block (measured) and serialises the peer
-            if (g.debug & 64) mbar_arrive_remote(&conv_bar[s], 0); else mbar_arrive_remote_relaxed(&conv_bar[s], 0);
+            if (HRB_DBG(64)) mbar_arrive_remote(&conv_bar[s], 0); else mbar_arrive_remote_relaxed(&conv_bar[s], 0);
             HRB_TRACE(4, it)
           }
         } else {
@@ -521,7 +529,7 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
             : "r"(taddr));
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         const int n0 = nt * BN + c0;
-        if (n0 >= g.N || (g.debug & 1)) continue;  // uniform: the whole sub-tile is outside the matrix
+        if (n0 >= g.N || (HRB_DBG(1))) continue;  // uniform: the whole sub-tile is outside the matrix
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
@@ -687,6 +695,7 @@ static void dump_trace(long long* d_trace, cudaStream_t st) {
 
 // The cta_group::2 kernel (two CTAs of a cluster share one 256 x 128 tile) is the default; HRB_TC_PAIR=0 selects the single-CTA one
 static bool pair_enabled() {
+#ifdef HRB_DEVTOOLS
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("HRB_TC_PAIR");
@@ -695,24 +704,29 @@ static bool pair_enabled() {
     if (a != nullptr && strcmp(a, "smem") == 0) v = 0;
   }
   return v != 0;
+#else
+  return true;
+#endif
 }
 
 template <int BN, int EPI, bool AMN = false>
 static int launch(const float* A, int64_t lda, const float* Bt, int64_t ldb, const Args& g_in, cudaStream_t st) {
   Args g = g_in;
+  long long* d_trace = nullptr;
+#ifdef HRB_DEVTOOLS
   static int dbg = -1;
   if (dbg < 0) {
     const char* e = getenv("HRB_TC_DEBUG");
     dbg = e ? atoi(e) : 0;
   }
   g.debug = dbg;
-  static long long* d_trace = nullptr;
+  static long long* d_trace_buf = nullptr;
   static int want_trace = -1;
   if (want_trace < 0) {
     want_trace = getenv("HRB_TC_TRACE") != nullptr ? 1 : 0;
-    if (want_trace) cudaMalloc((void**)&d_trace, 2 * 8 * 64 * sizeof(long long));
+    if (want_trace) cudaMalloc((void**)&d_trace_buf, 2 * 8 * 64 * sizeof(long long));
   }
-  g.trace = d_trace;
+  d_trace = d_trace_buf;
   if (d_trace != nullptr) cudaMemsetAsync(d_trace, 0, 2 * 8 * 64 * sizeof(long long), st);
   // HRB_TC_A=smem keeps the A tile's hi/lo halves in shared memory (the first version of the kernel; not for the untransposed-A form)
   static int a_tmem = -1;
@@ -720,6 +734,11 @@ static int launch(const float* A, int64_t lda, const float* Bt, int64_t ldb, con
     const char* e = getenv("HRB_TC_A");
     a_tmem = (e != nullptr && strcmp(e, "smem") == 0) ? 0 : 1;
   }
+#else
+  g.debug = 0;
+  const int a_tmem = 1;
+#endif
+  g.trace = d_trace;
   if (AMN && !a_tmem) return fail(HRB_UNSUPPORTED, "tcgen05 GEMM: the untransposed-A weight gradient needs A in tensor memory (unset HRB_TC_A)");
   const bool pair = a_tmem && pair_enabled();
   CUtensorMap ma, mb, mc, mct;

@@ -191,7 +191,6 @@ HRB_API int hrb_lau_fwd(const float* table, int64_t vocab, int32_t dim, const in
     if (act == HRB_ACT_DICE_ && l != n_layers - 1) off += 3 * (int64_t)out;
     off = (off + 3) / 4 * 4;  // keep every W 16-byte aligned
     if (out > maxw) maxw = out;
-    if (out % 4 != 0 && out != 1 && false) return HRB_UNSUPPORTED;
     in = out;
   }
   const int pitch = maxw + 4;

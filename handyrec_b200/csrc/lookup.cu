@@ -13,6 +13,7 @@
 // ONE row-major matrix out[B, out_ld] whose column blocks are the features in reference order, so
 // the DNN input (B, sum D) and the FM input (B, F, D) are the same bytes (layers/utils.py:40-96).
 #include <cub/device/device_radix_sort.cuh>
+#include <algorithm>
 #include <new>
 #include <stdlib.h>
 #include <string.h>
@@ -20,63 +21,7 @@
 
 #include "common.cuh"
 
-namespace hrb {
-
-struct FieldDev {
-  const float* table;
-  int64_t rows;
-  uint32_t key_base;  // first key of this field's table in the global (table,row) key space
-  int32_t dim;
-  int32_t seq_len;
-  int32_t pool;
-  int32_t ids_col;
-  int32_t out_col;
-  int32_t pos_col;  // first column in the dense position space (prefix sum of seq_len)
-  int32_t table_idx;
-};
-
-struct TableDev {
-  float* w;
-  float* m;
-  float* v;
-  int64_t rows;
-  uint32_t key_base;
-  int32_t dim;
-  float* grad;  // non-null: a13 adds the row's gradient sum here instead of updating the row (hrb_plan_set_dense_grads)
-};
-
-}  // namespace hrb
-
-struct hrb_plan {
-  int32_t n_tables = 0, n_fields = 0;
-  std::vector<hrb_table_desc> tables;
-  std::vector<hrb_field_desc> fields;
-  std::vector<hrb::FieldDev> fdev_host;
-  std::vector<hrb::TableDev> tdev_host;
-  uint64_t total_rows = 0;
-  int key_bits = 1;
-  int32_t pos_cols = 0;    // sum of seq_len
-  int32_t out_chunks = 0;  // sum of dim/4
-  int32_t max_dim = 0;
-  bool uniform_dim = true;
-  bool contiguous_out = true;  // out_col_f == out_col_0 + f*D (needs uniform_dim)
-  bool all_len1 = true;
-  bool has_max = false;
-  // device copies (one allocation)
-  void* dev_blob = nullptr;
-  hrb::FieldDev* d_fields = nullptr;
-  hrb::TableDev* d_tables = nullptr;
-  int32_t* d_chunk_field = nullptr;  // out chunk -> field
-  int32_t* d_chunk_q = nullptr;      // out chunk -> 4-column group inside the field
-  int32_t* d_pos_field = nullptr;    // position column -> field
-  uint32_t* d_hot_keys = nullptr;    // keys of every row of the tiny ("hot") tables (see bwd_hot_kernel)
-  int32_t n_hot_keys = 0;
-  std::vector<uint32_t> hot_lo, hot_len;
-  // row-sharded tables read over NVLink peer mappings (hrb_plan_set_peers): owner = id % n_ranks, local row = id / n_ranks
-  int32_t n_ranks = 1;
-  const float** d_peer_tab = nullptr;  // [n_ranks][n_tables] device pointers (peer-mapped for the other ranks)
-  int64_t* d_full_rows = nullptr;      // [n_tables] full vocabulary sizes
-};
+#include "plan.cuh"
 
 namespace hrb {
 
@@ -693,37 +638,7 @@ __device__ __forceinline__ void apply_row(const ApplyCtx& c, uint32_t key, int q
   }
   const int ti = find_table(c.tables, c.n_tables, key);
   const TableDev& t = c.tables[ti];
-  if (q * 4 >= t.dim) return;
-  const int64_t off = (int64_t)(key - t.key_base) * (t.dim >> 2) + q;
-  if (t.grad != nullptr) {  // dense-updated table: hand the gradient sum to the caller's dense optimiser step
-    float4* gp = reinterpret_cast<float4*>(t.grad) + off;
-    float4 o = *gp;
-    o.x += g.x; o.y += g.y; o.z += g.z; o.w += g.w;
-    *gp = o;
-    return;
-  }
-  float4* wp = reinterpret_cast<float4*>(t.w) + off;
-  float4 w = *wp;
-  const float l2 = c.opt.l2_scale;
-  g.x = fmaf(l2, w.x, g.x); g.y = fmaf(l2, w.y, g.y); g.z = fmaf(l2, w.z, g.z); g.w = fmaf(l2, w.w, g.w);
-  if (MODE == 0) {
-    const float lr = c.opt.lr;
-    w.x -= lr * g.x; w.y -= lr * g.y; w.z -= lr * g.z; w.w -= lr * g.w;
-  } else {
-    float4* mp = reinterpret_cast<float4*>(t.m) + off;
-    float4* vp = reinterpret_cast<float4*>(t.v) + off;
-    float4 m = *mp, v = *vp;
-    const float b1 = c.opt.beta1, b2 = c.opt.beta2, e = c.opt.eps, lr = c.lr_t;
-    m.x = b1 * m.x + (1.f - b1) * g.x; m.y = b1 * m.y + (1.f - b1) * g.y;
-    m.z = b1 * m.z + (1.f - b1) * g.z; m.w = b1 * m.w + (1.f - b1) * g.w;
-    v.x = b2 * v.x + (1.f - b2) * g.x * g.x; v.y = b2 * v.y + (1.f - b2) * g.y * g.y;
-    v.z = b2 * v.z + (1.f - b2) * g.z * g.z; v.w = b2 * v.w + (1.f - b2) * g.w * g.w;
-    w.x -= lr * m.x / (sqrtf(v.x) + e); w.y -= lr * m.y / (sqrtf(v.y) + e);
-    w.z -= lr * m.z / (sqrtf(v.z) + e); w.w -= lr * m.w / (sqrtf(v.w) + e);
-    *mp = m;
-    *vp = v;
-  }
-  *wp = w;
+  apply_table_row<MODE>(t, c.opt, c.lr_t, (int64_t)(key - t.key_base), q, g);
 }
 
 // Rows of tiny tables (vocab <= HOT_MAX_ROWS) collect thousands of duplicates per step (65536/V each at the Criteo
@@ -1175,7 +1090,24 @@ HRB_API int hrb_plan_create(const hrb_table_desc* tables_host, int32_t n_tables,
   const size_t sz_f = align_up(sizeof(FieldDev) * n_fields), sz_t = align_up(sizeof(TableDev) * n_tables);
   const size_t sz_c = align_up(sizeof(int32_t) * chunk_field.size()), sz_p = align_up(sizeof(int32_t) * pos_field.size());
   const size_t sz_h = align_up(sizeof(uint32_t) * (hot_keys.size() + 1));
-  const size_t total = sz_f + sz_t + 2 * sz_c + sz_p + sz_h;
+  // position columns grouped by table (embedding_bwd.cu: a unit scans every column of its table)
+  std::vector<ColDev> cols;
+  p->col_start_host.assign(n_tables + 1, 0);
+  p->unit_path_ok = true;
+  for (int t = 0; t < n_tables; ++t) {
+    p->col_start_host[t] = (int32_t)cols.size();
+    for (int f = 0; f < n_fields; ++f) {
+      if (p->fields[f].table != t) continue;
+      for (int l = 0; l < p->fields[f].seq_len; ++l)
+        cols.push_back(ColDev{p->fdev_host[f].pos_col + l, p->fields[f].out_col, f, 0});
+      if (p->fields[f].pool == HRB_POOL_MEAN) p->has_mean = true;
+    }
+    const int g = p->tdev_host[t].dim / 4;
+    if ((int)cols.size() - p->col_start_host[t] > 256 || (g & (g - 1)) != 0 || g > 32) p->unit_path_ok = false;
+  }
+  p->col_start_host[n_tables] = (int32_t)cols.size();
+  const size_t sz_cols = align_up(sizeof(ColDev) * (cols.size() + 1)), sz_cs = align_up(sizeof(int32_t) * (n_tables + 1));
+  const size_t total = sz_f + sz_t + 2 * sz_c + sz_p + sz_h + sz_cols + sz_cs;
   std::vector<char> blob(total, 0);
   memcpy(blob.data(), p->fdev_host.data(), sizeof(FieldDev) * n_fields);
   memcpy(blob.data() + sz_f, p->tdev_host.data(), sizeof(TableDev) * n_tables);
@@ -1183,6 +1115,8 @@ HRB_API int hrb_plan_create(const hrb_table_desc* tables_host, int32_t n_tables,
   memcpy(blob.data() + sz_f + sz_t + sz_c, chunk_q.data(), sizeof(int32_t) * chunk_q.size());
   memcpy(blob.data() + sz_f + sz_t + 2 * sz_c, pos_field.data(), sizeof(int32_t) * pos_field.size());
   if (!hot_keys.empty()) memcpy(blob.data() + sz_f + sz_t + 2 * sz_c + sz_p, hot_keys.data(), sizeof(uint32_t) * hot_keys.size());
+  if (!cols.empty()) memcpy(blob.data() + sz_f + sz_t + 2 * sz_c + sz_p + sz_h, cols.data(), sizeof(ColDev) * cols.size());
+  memcpy(blob.data() + sz_f + sz_t + 2 * sz_c + sz_p + sz_h + sz_cols, p->col_start_host.data(), sizeof(int32_t) * (n_tables + 1));
   cudaError_t e = cudaMalloc(&p->dev_blob, total);
   if (e == cudaSuccess) e = cudaMemcpy(p->dev_blob, blob.data(), total, cudaMemcpyHostToDevice);
   if (e != cudaSuccess) {
@@ -1197,6 +1131,8 @@ HRB_API int hrb_plan_create(const hrb_table_desc* tables_host, int32_t n_tables,
   p->d_chunk_q = (int32_t*)(d + sz_f + sz_t + sz_c);
   p->d_pos_field = (int32_t*)(d + sz_f + sz_t + 2 * sz_c);
   p->d_hot_keys = (uint32_t*)(d + sz_f + sz_t + 2 * sz_c + sz_p);
+  p->d_cols = (ColDev*)(d + sz_f + sz_t + 2 * sz_c + sz_p + sz_h);
+  p->d_col_start = (int32_t*)(d + sz_f + sz_t + 2 * sz_c + sz_p + sz_h + sz_cols);
   *plan_out = p;
   return HRB_OK;
 }
@@ -1206,6 +1142,7 @@ HRB_API int hrb_plan_destroy(hrb_plan* plan) {
   if (plan->dev_blob) cudaFree(plan->dev_blob);
   if (plan->d_peer_tab) cudaFree((void*)plan->d_peer_tab);
   if (plan->d_full_rows) cudaFree(plan->d_full_rows);
+  if (plan->units.d_blob) cudaFree(plan->units.d_blob);
   delete plan;
   return HRB_OK;
 }
@@ -1229,11 +1166,15 @@ static int launch_rows(const hrb_plan* plan, const int32_t* ids, int64_t ids_ld,
                        float* fm_sum, int32_t* oob, cudaStream_t st) {
   const int G = plan->max_dim / 4;
   // v2 tile kernel for plain-lookup groups laid out contiguously (the Criteo shape)
+#ifdef HRB_DEVTOOLS
   static int use_tile = -1;
   if (use_tile < 0) {
     const char* e = getenv("HRB_LOOKUP_KERNEL");
     use_tile = (e != nullptr && strcmp(e, "rows") == 0) ? 0 : 1;
   }
+#else
+  const int use_tile = 1;
+#endif
   if (use_tile && inv_count == nullptr && plan->all_len1 && plan->contiguous_out && (G == 2 || G == 4 || G == 8 || G == 16) && aligned16(out) &&
       (out_ld % 4 == 0) && (plan->fdev_host[0].out_col % 4 == 0)) {
     int pitch = plan->n_fields * plan->max_dim;       // floats
@@ -1343,6 +1284,7 @@ HRB_API int hrb_lookup_bwd_workspace(const hrb_plan* plan, int64_t ids_ld, int64
   int rc = carve_bwd_ws(n > 0 ? n : 1, batch * plan->n_fields + 1, plan->max_dim, plan->key_bits, nullptr, w);
   if (rc != HRB_OK) return rc;
   *bytes = w.total;
+  if (unit_path_supported(plan, batch)) *bytes = std::max(w.total, unit_workspace_bytes(plan, batch));
   return HRB_OK;
 }
 
@@ -1364,6 +1306,8 @@ HRB_API int hrb_lookup_bwd_update(const hrb_plan* plan, const int32_t* ids, int6
   if (batch == 0) return HRB_OK;
   const int64_t n = batch * plan->pos_cols;
   HRB_REQUIRE(n < 0x7FFFFFFFll, "hrb_lookup_bwd_update: batch*sum(seq_len) exceeds 2^31-1");
+  if (plan->bwd_algo != HRB_BWD_SORT && unit_path_supported(plan, batch))  // two-level partition, one CTA per row range (embedding_bwd.cu)
+    return run_unit_update(plan, ids, ids_ld, batch, dout, dout_ld, *opt_host, workspace, workspace_bytes, (cudaStream_t)stream);
   BwdWorkspace w;
   int rc = carve_bwd_ws(n, batch * plan->n_fields + 1, plan->max_dim, plan->key_bits, workspace, w);
   if (rc != HRB_OK) return rc;
@@ -1476,19 +1420,25 @@ HRB_API int hrb_lookup_combine(const hrb_plan* plan, const float* psum, const fl
 // =============================================================================================
 namespace hrb {
 
+__device__ __forceinline__ bool routed_id_valid(const FieldDev& f, int32_t id, const int64_t* __restrict__ full_rows) {
+  return (f.pool == HRB_POOL_NONE || id != 0) && id >= 0 && (full_rows == nullptr || (int64_t)id < full_rows[f.table_idx]);
+}
+
 // one thread per (sample, position column): owner rank and the key in the OWNER's shard key space
 __global__ void __launch_bounds__(256) route_kernel(const FieldDev* __restrict__ fields, const int32_t* __restrict__ pos_field,
                                                    int32_t pos_cols, const int32_t* __restrict__ ids, int64_t ids_ld, int64_t batch,
                                                    int32_t n_ranks, const uint32_t* __restrict__ key_base /* [n_ranks][n_tables] */,
-                                                   int32_t n_tables, uint32_t* __restrict__ owner, uint32_t* __restrict__ key,
-                                                   uint32_t* __restrict__ pos) {
+                                                   int32_t n_tables, const int64_t* __restrict__ full_rows, uint32_t* __restrict__ owner,
+                                                   uint32_t* __restrict__ key, uint32_t* __restrict__ pos) {
   const int64_t total = batch * pos_cols;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t b = i / pos_cols;
     const int c = (int)(i - b * pos_cols);
     const FieldDev& f = fields[pos_field[c]];
     const int32_t id = ids[b * ids_ld + f.ids_col + (c - f.pos_col)];
-    const bool valid = (f.pool == HRB_POOL_NONE || id != 0) && id >= 0;
+    // same validity rule as the single-GPU path (bwd_prep_kernel / the forward): padding, negative and out-of-vocabulary ids
+    // are nobody's; without the full vocabulary sizes (hrb_plan_set_full_rows) only the lower bound can be checked
+    const bool valid = routed_id_valid(f, id, full_rows);
     const uint32_t o = valid ? (uint32_t)(id % n_ranks) : (uint32_t)n_ranks;  // n_ranks = "nobody": sorts last
     owner[i] = o;
     key[i] = valid ? key_base[o * n_tables + f.table_idx] + (uint32_t)(id / n_ranks) : 0xFFFFFFFFu;
@@ -1561,7 +1511,7 @@ __global__ void __launch_bounds__(256) scatter_rows_kernel(const FieldDev* __res
 __global__ void __launch_bounds__(256) pool_positions_kernel(const FieldDev* __restrict__ fields, int32_t n_fields, int32_t pos_cols,
                                                             int32_t chunks, const int32_t* __restrict__ ids, int64_t ids_ld,
                                                             int64_t batch, const float* __restrict__ pos_rows,
-                                                            float* __restrict__ out, int64_t out_ld) {
+                                                            float* __restrict__ out, int64_t out_ld, const int64_t* __restrict__ full_rows) {
   const int64_t total = batch * n_fields * chunks;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int q = (int)(i % chunks);
@@ -1575,7 +1525,7 @@ __global__ void __launch_bounds__(256) pool_positions_kernel(const FieldDev* __r
     float4 acc = f.pool == HRB_POOL_MAX ? make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY) : make_float4(0.f, 0.f, 0.f, 0.f);
     float cnt = 0.f;
     for (int l = 0; l < f.seq_len; ++l) {
-      if (idp[l] != 0) {
+      if (routed_id_valid(f, idp[l], full_rows)) {
         const float4 v = __ldg(pr + (int64_t)l * chunks);
         cnt += 1.f;
         if (f.pool == HRB_POOL_MAX) {
@@ -1599,7 +1549,8 @@ __global__ void __launch_bounds__(256) pool_positions_kernel(const FieldDev* __r
 __global__ void __launch_bounds__(256) gather_grads_kernel(const FieldDev* __restrict__ fields, const int32_t* __restrict__ pos_field,
                                                           int32_t pos_cols, int32_t chunks, const int32_t* __restrict__ ids,
                                                           int64_t ids_ld, const uint32_t* __restrict__ perm, int64_t n,
-                                                          const float* __restrict__ dout, int64_t dout_ld, float* __restrict__ send) {
+                                                          const float* __restrict__ dout, int64_t dout_ld, float* __restrict__ send,
+                                                          const int64_t* __restrict__ full_rows) {
   const int64_t total = n * chunks;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t j = i / chunks;
@@ -1612,7 +1563,7 @@ __global__ void __launch_bounds__(256) gather_grads_kernel(const FieldDev* __res
     if (f.pool == HRB_POOL_MEAN) {
       const int32_t* idp = ids + b * ids_ld + f.ids_col;
       int cnt = 0;
-      for (int l = 0; l < f.seq_len; ++l) cnt += idp[l] != 0;
+      for (int l = 0; l < f.seq_len; ++l) cnt += routed_id_valid(f, idp[l], full_rows);
       s = cnt > 0 ? __fdiv_rn(1.0f, (float)cnt) : 0.f;
     }
     float4 v = __ldg(reinterpret_cast<const float4*>(dout + b * dout_ld + f.out_col) + q);
@@ -1667,7 +1618,7 @@ HRB_API int hrb_route_ids(const hrb_plan* plan, const int32_t* ids, int64_t ids_
   uint32_t* owner_sorted = (uint32_t*)((char*)workspace + 3 * seg);
   void* cub_tmp = (char*)workspace + 4 * seg;
   route_kernel<<<grid_for(n, 256), 256, 0, st>>>(plan->d_fields, plan->d_pos_field, plan->pos_cols, ids, ids_ld, batch, n_ranks, key_base,
-                                               plan->n_tables, owner, key, pos);
+                                               plan->n_tables, plan->d_full_rows, owner, key, pos);
   HRB_LAUNCH_CHECK();
   int bits = 1;
   while ((1 << bits) <= n_ranks) ++bits;
@@ -1707,7 +1658,7 @@ HRB_API int hrb_scatter_rows(const hrb_plan* plan, const int32_t* ids, int64_t i
   }
   if (!plan->all_len1 && batch > 0) {
     pool_positions_kernel<<<grid_for(batch * plan->n_fields * chunks, 256), 256, 0, st>>>(plan->d_fields, plan->n_fields, plan->pos_cols,
-                                                                                         chunks, ids, ids_ld, batch, pos_rows, out, out_ld);
+                                                                                         chunks, ids, ids_ld, batch, pos_rows, out, out_ld, plan->d_full_rows);
     HRB_LAUNCH_CHECK();
   }
   return HRB_OK;
@@ -1721,7 +1672,7 @@ HRB_API int hrb_gather_grads(const hrb_plan* plan, const int32_t* ids, int64_t i
   if (!plan->uniform_dim || plan->has_max) return fail(HRB_UNSUPPORTED, "hrb_gather_grads: needs one embedding dim and no max pooling");
   const int chunks = plan->max_dim / 4;
   gather_grads_kernel<<<grid_for(n * chunks, 256), 256, 0, (cudaStream_t)stream>>>(plan->d_fields, plan->d_pos_field, plan->pos_cols, chunks,
-                                                                                  ids, ids_ld, perm, n, dout, dout_ld, send);
+                                                                                  ids, ids_ld, perm, n, dout, dout_ld, send, plan->d_full_rows);
   HRB_LAUNCH_CHECK();
   return HRB_OK;
 }
@@ -1794,5 +1745,21 @@ HRB_API int hrb_plan_set_peers(hrb_plan* plan, int32_t n_ranks, const void* cons
   HRB_CUDA(cudaMemcpy((void*)plan->d_peer_tab, peer_tables_host, np * sizeof(void*), cudaMemcpyHostToDevice));
   HRB_CUDA(cudaMemcpy(plan->d_full_rows, full_rows_host, plan->n_tables * sizeof(int64_t), cudaMemcpyHostToDevice));
   plan->n_ranks = n_ranks;
+  return HRB_OK;
+}
+
+// Full vocabulary sizes of the tables of a plan whose `rows` are shard sizes (the requester side of the row exchange):
+// hrb_route_ids / hrb_scatter_rows / hrb_gather_grads then treat ids >= full_rows[table] as invalid, exactly like the
+// single-GPU path does with `rows`.
+HRB_API int hrb_plan_set_full_rows(hrb_plan* plan, const int64_t* full_rows_host) {
+  HRB_REQUIRE(plan && full_rows_host, "hrb_plan_set_full_rows: bad argument");
+  if (plan->d_full_rows == nullptr) HRB_CUDA(cudaMalloc((void**)&plan->d_full_rows, plan->n_tables * sizeof(int64_t)));
+  HRB_CUDA(cudaMemcpy(plan->d_full_rows, full_rows_host, plan->n_tables * sizeof(int64_t), cudaMemcpyHostToDevice));
+  return HRB_OK;
+}
+
+HRB_API int hrb_plan_set_bwd_algo(hrb_plan* plan, int32_t algo) {
+  HRB_REQUIRE(plan && algo >= HRB_BWD_AUTO && algo <= HRB_BWD_SORT, "hrb_plan_set_bwd_algo: bad argument");
+  plan->bwd_algo = algo;
   return HRB_OK;
 }

@@ -33,6 +33,29 @@ __global__ void __launch_bounds__(256) sigmoid_bce_kernel(const float* __restric
   }
 }
 
+// Keras binary_crossentropy on PROBABILITIES (no cached logits): p is clipped to [eps, 1-eps]; the gradient of the clip is 0 outside
+__global__ void __launch_bounds__(256) clipped_bce_kernel(const float* __restrict__ prob, const float* __restrict__ label, int64_t n,
+                                                         float eps, float grad_scale, float* __restrict__ dprob,
+                                                         float* __restrict__ loss_sum) {
+  __shared__ float red[8];
+  float local = 0.f;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float p0 = prob[i], y = label[i];
+    const float p = fminf(fmaxf(p0, eps), 1.0f - eps);
+    local -= y * logf(p) + (1.0f - y) * logf(1.0f - p);
+    if (dprob != nullptr) dprob[i] = (p0 >= eps && p0 <= 1.0f - eps) ? ((1.0f - y) / (1.0f - p) - y / p) * grad_scale : 0.f;
+  }
+  local = warp_sum(local);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = local;
+  __syncthreads();
+  if (threadIdx.x == 0 && loss_sum != nullptr) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += red[k];
+    atomicAdd(loss_sum, t);
+  }
+}
+
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                                   float* __restrict__ v, int64_t n, float lr_t, float b1, float b2,
                                                   float eps, float l2_scale) {
@@ -197,6 +220,15 @@ HRB_API int hrb_sigmoid_bce(const float* dnn_logit, const float* fm_logit, const
   if (batch == 0) return HRB_OK;
   sigmoid_bce_kernel<<<ew_grid(batch), 256, 0, (cudaStream_t)stream>>>(dnn_logit, fm_logit, label, batch, grad_scale, prob,
                                                                       dlogit, loss_sum);
+  HRB_LAUNCH_CHECK();
+  return HRB_OK;
+}
+
+HRB_API int hrb_clipped_bce(const float* prob, const float* label, int64_t n, float eps, float grad_scale, float* dprob,
+                            float* loss_sum, void* stream) {
+  HRB_REQUIRE(prob && label && n >= 0, "hrb_clipped_bce: null/negative argument");
+  if (n == 0) return HRB_OK;
+  clipped_bce_kernel<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(prob, label, n, eps, grad_scale, dprob, loss_sum);
   HRB_LAUNCH_CHECK();
   return HRB_OK;
 }

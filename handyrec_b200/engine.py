@@ -323,10 +323,35 @@ class DeepFMEngine:
         if self.n_params > self.n_dense_params:
             self.grads[self.n_dense_params :].zero_()
 
+    # The library has two implementations of the embedding backward (hrb200.h: hrb_bwd_algo); which one is faster depends on the
+    # id distribution (spread ids: UNITS, a few very hot rows: SORT).  The engine times both on the caller's own data during
+    # its first steps (steps 3-6, one host sync each) and keeps the faster one; both are deterministic and agree to rounding.
+    autotune_embedding_bwd = True
+    _bwd_trials: Optional[list] = None
+    bwd_algo = "auto"
+
     def _embedding_backward(self, ids, B, st, op) -> None:
         self._zero_table_grads()
+        trial = None
+        if self.autotune_embedding_bwd and self._marks is None and B == self.B and 3 <= self.step_count <= 6:
+            trial = _lib.BWD_UNITS if self.step_count % 2 else _lib.BWD_SORT
+            call("hrb_plan_set_bwd_algo", self.plan._h, trial)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
         call("hrb_lookup_bwd_update", self.plan._h, K._p(ids), ids.stride(0), B, K._p(self.dX0), self.K0p, None, ctypes.byref(op),
              K._p(self._ws_emb), self._ws_emb.numel(), st)
+        if trial is not None:
+            e1.record()
+            e1.synchronize()
+            self._bwd_trials = (self._bwd_trials or []) + [(trial, e0.elapsed_time(e1))]
+            if self.step_count == 6:
+                best = {}
+                for algo, ms in self._bwd_trials:
+                    best[algo] = min(best.get(algo, 1e30), ms)
+                pick = min(best, key=best.get)
+                call("hrb_plan_set_bwd_algo", self.plan._h, pick)
+                self.bwd_algo = "units" if pick == _lib.BWD_UNITS else "sort"
+                self.bwd_algo_ms = {("units" if a == _lib.BWD_UNITS else "sort"): round(m, 4) for a, m in best.items()}
         self._mark("embedding_bwd_update")
 
     def _pre_embedding_backward(self) -> None:

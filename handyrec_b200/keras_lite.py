@@ -311,7 +311,11 @@ def binary_crossentropy(y_true, y_pred):
 
     logits = getattr(y_pred, "_keras_logits", None)
     if logits is None:
-        raise ValueError("binary_crossentropy expects the output of a sigmoid Activation (its logits are used, as in Keras)")
+        # Keras' fallback when the prediction is not the direct output of a sigmoid (e.g. BatchNormalization / Dropout behind the
+        # output activation, layers/core.py:66-73): probabilities clipped to [eps, 1-eps], eps = 1e-7
+        from .autograd_ops import ClippedBCEFn
+
+        return ClippedBCEFn.apply(y_pred, y_true)
     return SigmoidBCEFn.apply(logits, y_true)
 
 

@@ -54,6 +54,9 @@ class CudaShardProvider:
         self.plan, self.N, self.dev = plan, n_ranks, plan.device
         self.D = plan.tables[0].shape[1]
         self.kb = key_base_table(vocabs, n_ranks).to(torch.int32).to(self.dev)  # values < 2^31
+        # the plan's tables are SHARDS: give the routing kernels the full vocabulary sizes so that an out-of-vocabulary id is
+        # dropped here exactly like on the single-GPU path instead of landing in another table's key range
+        call("hrb_plan_set_full_rows", plan._h, (ctypes.c_int64 * len(vocabs))(*[int(v) for v in vocabs]))
         need = ctypes.c_size_t(0)
         call("hrb_route_workspace", plan._h, batch, ctypes.byref(need))
         self.ws_route = torch.empty(need.value, device=self.dev, dtype=torch.uint8)
@@ -169,10 +172,18 @@ class RowExchange:
         self._counts_dev = counts
         self._recv_counts_dev = self.comm.all_to_all_equal(counts[: self.N].contiguous())
         self._routed = False
+        # the routing may have been issued on a side stream: whoever consumes perm / send_keys / the counts first makes ITS
+        # stream wait for this event (finish_route), so a caller on another stream never reads them half-written
+        self._route_done = None
+        if self.perm.is_cuda:
+            self._route_done = torch.cuda.Event()
+            self._route_done.record()
 
     def finish_route(self) -> None:
         if self._routed:
             return
+        if getattr(self, "_route_done", None) is not None:
+            torch.cuda.current_stream().wait_event(self._route_done)
         both = torch.cat([self._counts_dev[: self.N], self._recv_counts_dev]).tolist()  # the one host sync of the step
         self.send_counts, self.recv_counts = [int(x) for x in both[: self.N]], [int(x) for x in both[self.N :]]
         self.n_send, self.n_recv = sum(self.send_counts), sum(self.recv_counts)
@@ -190,6 +201,8 @@ class RowExchange:
         """Gather this rank's per-position gradient rows and put them on the wire; work issued to the current stream after
         this call overlaps the transfer."""
         self.finish_route()
+        if getattr(self, "_route_done", None) is not None:  # finish_route may have run earlier, on another stream
+            torch.cuda.current_stream().wait_event(self._route_done)
         self._grad_send = self.p.gather_grads(ids, self.perm, self.n_send, dout)
         start = getattr(self.comm, "all_to_all_v_start", None)
         if start is not None:

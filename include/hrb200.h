@@ -155,6 +155,15 @@ int hrb_lookup_bwd_update(const hrb_plan* plan, const int32_t* ids, int64_t ids_
                           const hrb_opt_params* opt_host, void* workspace, size_t workspace_bytes,
                           void* stream);
 
+/* Two implementations of hrb_lookup_bwd_update with identical semantics (both deterministic, no atomics on gradients):
+ *   UNITS  two-level radix partition; the second level (one CTA per row range) sorts in shared memory and is fused with the
+ *          segmented reduction and the row update (csrc/embedding_bwd.cu) -- fastest when ids spread over the tables;
+ *   SORT   global radix sort of (table,row) keys, then chunked segmented reduction + merge (csrc/lookup.cu) -- robust when a
+ *          few rows collect most of the batch (Zipf ids).
+ * AUTO = UNITS whenever the plan / batch is covered by it.  The host may time both on its own data and pin one. */
+typedef enum hrb_bwd_algo { HRB_BWD_AUTO = 0, HRB_BWD_UNITS = 1, HRB_BWD_SORT = 2 } hrb_bwd_algo;
+int hrb_plan_set_bwd_algo(hrb_plan* plan, int32_t algo);
+
 /* Dense-updated tables: grads_host[t] != NULL (rows*dim fp32, 16-byte aligned) makes hrb_lookup_bwd_update ADD the
  * per-row gradient sums of table t into that buffer and leave weight/moments alone -- the caller zeroes the buffer,
  * (all-reduces it when the table is replicated over ranks) and runs its dense optimiser step over the table, which is
@@ -278,6 +287,12 @@ int hrb_att_pool_bwd(const float* s, const float* k, const float* dout, int64_t 
 int hrb_sigmoid_bce(const float* dnn_logit, const float* fm_logit, const float* label, int64_t batch,
                     float grad_scale, float* prob, float* dlogit, float* loss_sum, void* stream);
 
+/* Keras binary_crossentropy on probabilities (the fallback Keras takes when the prediction is not the direct output of a sigmoid,
+ * e.g. DNN(..., use_bn=True, output_activation="sigmoid"): layers/core.py:66-73 puts BN / Dropout behind the activation):
+ *   p = clip(prob, eps, 1-eps); loss_sum += -(y log p + (1-y) log(1-p)); dprob = d loss / d prob * grad_scale (0 where clipped). */
+int hrb_clipped_bce(const float* prob, const float* label, int64_t n, float eps, float grad_scale, float* dprob,
+                    float* loss_sum, void* stream);
+
 /* a8 concat glue (layers/utils.py:28-36,70-84): dense features (fp32, or int32 cast to fp32) go to the
  * head columns of the DNN input row; columns [n, n_pad) are zero-filled (alignment padding). */
 int hrb_pack_dense(const void* src, int32_t src_is_int32, int64_t src_ld, int64_t batch, int32_t n, int32_t n_pad,
@@ -319,6 +334,9 @@ int hrb_lookup_combine(const hrb_plan* plan, const float* psum, const float* pco
  * EVERY rank is replicated: its rows are read from the plan's own copy (hrb_table_desc.weight, full row count). */
 int hrb_enable_peer_access(int32_t peer_device); /* cudaDeviceEnablePeerAccess from the current device, idempotent */
 int hrb_plan_set_peers(hrb_plan* plan, int32_t n_ranks, const void* const* peer_tables_host, const int64_t* full_rows_host);
+/* Requester-side plans hold SHARD row counts; with the full vocabulary sizes set, the routing helpers below skip ids outside
+ * [0, full_rows[table]) exactly like the single-GPU path skips ids outside [0, rows) (TF-GPU gather semantics, a5). */
+int hrb_plan_set_full_rows(hrb_plan* plan, const int64_t* full_rows_host);
 int hrb_route_workspace(const hrb_plan* plan, int64_t batch, size_t* bytes);
 int hrb_route_ids(const hrb_plan* plan, const int32_t* ids, int64_t ids_ld, int64_t batch, int32_t n_ranks,
                   const uint32_t* key_base, uint32_t* perm, uint32_t* send_keys, int64_t* counts, void* workspace,

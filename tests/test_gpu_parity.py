@@ -398,6 +398,98 @@ def test_shared_table_two_fields_bwd(dev):
     close(dt, table - 0.5 * leaf.grad, GRAD_TOL)
 
 
+def _zipf_ids(B, V, a, seed):
+    """Zipf(a) over [1, V): inverse CDF of the continuous approximation (bench.py --ids zipf)."""
+    g = torch.Generator().manual_seed(seed)
+    u = torch.rand(B, generator=g, dtype=torch.float64)
+    x = ((V ** (1 - a) - 1) * u + 1) ** (1 / (1 - a))
+    return x.long().clamp_(1, V - 1).to(torch.int32)
+
+
+@pytest.mark.parametrize("opt", ["sgd", "adam"])
+@pytest.mark.parametrize("B,dist", [(65536, "zipf"), (30001, "uniform"), (65536, "onehot")])
+def test_group_lookup_bwd_unit_path_skew(dev, opt, B, dist):
+    """The sort-free backward (embedding_bwd.cu) under skew: Zipf ids (histogram splits, single hot rows inside big tables),
+    one id for the whole batch (a row with 65536 positions), tiny tables (slices), a batch that is not a multiple of 16;
+    a dense-updated table next to in-place ones; deterministic bit for bit."""
+    k = K()
+    D = 16
+    vocabs = [4, 11, 300, 5000, 250000, 2000000]
+    tables = [rnd(v, D, seed=v, scale=0.05) for v in vocabs]
+    if dist == "zipf":
+        ids = torch.stack([_zipf_ids(B, v, 1.05, 10 + f) for f, v in enumerate(vocabs)], 1)
+    elif dist == "uniform":
+        g = torch.Generator().manual_seed(2)
+        ids = torch.stack([torch.randint(0, v, (B,), generator=g, dtype=torch.int32) for v in vocabs], 1)
+    else:
+        ids = torch.stack([torch.full((B,), min(3, v - 1), dtype=torch.int32) for v in vocabs], 1)
+        ids[::7, 5] = 123456
+    dout = rnd(B, len(vocabs) * D, seed=3, scale=1.0 / 256)
+    fields = [(f, 1, "none", f, f * D) for f in range(len(vocabs))]
+    lr = 0.5
+
+    def run():
+        dt = [t.clone().to(dev) for t in tables]
+        ms = [torch.zeros_like(t) for t in dt] if opt == "adam" else None
+        vs = [torch.zeros_like(t) for t in dt] if opt == "adam" else None
+        plan = k.LookupPlan(dt, fields, adam_m=ms, adam_v=vs)
+        dense_g = torch.zeros_like(dt[3])
+        plan.set_dense_grads([None, None, None, dense_g, None, None])  # table 3 is "dense-updated": gradient sums only
+        plan.backward_update(ids.to(dev), dout.to(dev), opt=opt, lr=lr, step=1)
+        torch.cuda.synchronize()
+        return dt, dense_g
+
+    dt, dense_g = run()
+    for f, v in enumerate(vocabs):
+        gr = oracle.embedding_grad_dense(v, ids[:, f], dout[:, f * D : (f + 1) * D])
+        if f == 3:
+            close(dense_g, gr, GRAD_TOL)
+            assert torch.equal(dt[3].cpu(), tables[3])
+        elif opt == "sgd":
+            close(dt[f], tables[f] - lr * gr, GRAD_TOL)
+        else:
+            lr_t = lr * np.sqrt(1 - 0.999) / (1 - 0.9)
+            want = tables[f] - lr_t * (0.1 * gr) / ((0.001 * gr * gr).sqrt() + 1e-7)
+            touched = torch.zeros(v, dtype=torch.bool)
+            touched[ids[:, f].long()] = True
+            # rows whose summed gradient is ~0 make m/(sqrt(v)+eps) ill-conditioned: compare the well-conditioned ones
+            ok = (gr.abs() > 1e-6).all(1) | ~touched
+            close(dt[f].cpu()[ok], want[ok], 5e-4)
+            assert torch.equal(dt[f].cpu()[~touched], tables[f][~touched])
+    dt2, dense_g2 = run()
+    assert all(torch.equal(a, b) for a, b in zip(dt, dt2)) and torch.equal(dense_g, dense_g2), "backward is not deterministic"
+
+
+def test_group_lookup_bwd_unit_path_mixed_dims_and_sequences(dev):
+    """Tables of different widths (G = 2 and 8), a long mean-pooled history sharing its table with a plain feature, and a
+    sum-pooled one: every position of every column is reduced into the right row with the right 1/n_valid scale."""
+    k = K()
+    B = 4099
+    Vm, Vg, Vu = 3953, 19, 6041
+    Dm, Dg = 32, 8
+    t_m, t_g, t_u = rnd(Vm, Dm, seed=1, scale=0.05), rnd(Vg, Dg, seed=2, scale=0.05), rnd(Vu, Dm, seed=3, scale=0.05)
+    g = torch.Generator().manual_seed(5)
+    uid = torch.randint(0, Vu, (B, 1), generator=g, dtype=torch.int32)
+    mid = torch.randint(0, Vm, (B, 1), generator=g, dtype=torch.int32)
+    hist = rand_ids(B, 50, Vm, seed=6)
+    genres = rand_ids(B, 6, Vg, seed=7)
+    ids = torch.cat([uid, mid, hist, genres], 1)
+    leaf = [t.clone().requires_grad_(True) for t in (t_u, t_m, t_g)]
+    e_u, _ = oracle.custom_embedding(leaf[0], uid, False)
+    e_m, _ = oracle.custom_embedding(leaf[1], mid, True)
+    e_h = oracle.sequence_pooling(*oracle.custom_embedding(leaf[1], hist, True), "mean")
+    e_g = oracle.sequence_pooling(*oracle.custom_embedding(leaf[2], genres, True), "sum")
+    out = torch.cat([e_u[:, 0], e_m[:, 0], e_h[:, 0], e_g[:, 0]], 1)
+    dout = rnd(B, out.shape[1], seed=8)
+    (out * dout).sum().backward()
+    dt = [t.clone().to(dev) for t in (t_u, t_m, t_g)]
+    fields = [(0, 1, "none", 0, 0), (1, 1, "none", 1, Dm), (1, 50, "mean", 2, 2 * Dm), (2, 6, "sum", 52, 3 * Dm)]
+    plan = k.LookupPlan(dt, fields)
+    plan.backward_update(ids.to(dev), dout.to(dev), opt="sgd", lr=0.25)
+    for got, t0, lf in zip(dt, (t_u, t_m, t_g), leaf):
+        close(got, t0 - 0.25 * lf.grad, GRAD_TOL)
+
+
 # ------------------------------------------------------------------------------------------------
 # a11: Dense, Dice
 # ------------------------------------------------------------------------------------------------
@@ -552,3 +644,80 @@ def test_sharded_lookup_emulated(dev, n_ranks, pool):
     # and the oracle agrees
     o = oracle.sharded_lookup_emulated(t2, ids[:, 1:], n_ranks, pool)
     close(got[:, D:], o[:, 0], FWD_TOL if pool != "max" else 1e-4)
+
+
+# ------------------------------------------------------------------------------------------------
+# a11: BatchNormalization / Dropout inside DNN (layers/core.py:71-73)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("shape", [(777, 37), (64, 50, 36), (4096, 128), (3, 5)])
+@pytest.mark.parametrize("training", [True, False])
+def test_batchnorm_fwd_bwd(dev, shape, training):
+    """hrb_batchnorm_fwd/bwd against oracle.batch_norm + autograd: training (biased batch statistics over every axis but the
+    last) and inference (moving statistics), 2-D and 3-D inputs, affine parameters, Keras eps = 1e-3."""
+    from handyrec_b200.autograd_ops import BatchNormFn
+
+    u = shape[-1]
+    x = (rnd(*shape, seed=1) * 1.7 + 0.3).requires_grad_(True)
+    gamma = (1.0 + 0.2 * rnd(u, seed=2)).requires_grad_(True)
+    beta = (0.1 * rnd(u, seed=3)).requires_grad_(True)
+    mm, mv = 0.2 * rnd(u, seed=4), 0.5 + rnd(u, seed=5).abs()
+    dy = rnd(*shape, seed=6)
+    y, bm, bv = oracle.batch_norm(x, mm, mv, gamma, beta, 1e-3, training)
+    (y * dy).sum().backward()
+    xd = x.detach().to(dev).requires_grad_(True)
+    gd, bd = gamma.detach().to(dev).requires_grad_(True), beta.detach().to(dev).requires_grad_(True)
+    yd = BatchNormFn.apply(xd, gd, bd, mm.to(dev), mv.to(dev), training, 1e-3)
+    close(yd, y, FWD_TOL)
+    if training:
+        got_m, got_v = yd.grad_fn.batch_stats
+        close(got_m, bm, FWD_TOL)
+        close(got_v, bv, FWD_TOL)
+    (yd * dy.to(dev)).sum().backward()
+    close(xd.grad, x.grad, GRAD_TOL)
+    close(gd.grad, gamma.grad, GRAD_TOL)
+    close(bd.grad, beta.grad, GRAD_TOL)
+
+
+@pytest.mark.parametrize("rate", [0.1, 0.5, 0.9])
+def test_dropout_mask_scale_and_backward(dev, rate):
+    """hrb_dropout: survivors are scaled by exactly 1/(1-rate) (Keras Dropout in training mode), the keep mask is a pure function
+    of (seed, element index) -- so the backward (the same call on dy) uses the SAME mask, a second call reproduces it bit for
+    bit, another seed gives another mask -- and the keep fraction is 1-rate within sampling error."""
+    from handyrec_b200.autograd_ops import DropoutFn
+
+    n = 1 << 20
+    x = (rnd(n, seed=1).abs() + 0.5).to(dev).requires_grad_(True)
+    y = DropoutFn.apply(x, rate, 1234)
+    keep = y != 0
+    frac = float(keep.float().mean())
+    assert abs(frac - (1 - rate)) < 4 * np.sqrt(rate * (1 - rate) / n) + 1e-4, frac
+    want = torch.where(keep, x.detach() * np.float32(1.0 / (1.0 - rate)), torch.zeros_like(y))
+    assert torch.allclose(y.detach(), want, rtol=1e-6, atol=0)
+    assert torch.equal(y.detach(), DropoutFn.apply(x.detach(), rate, 1234))
+    assert not torch.equal(keep, DropoutFn.apply(x.detach(), rate, 1235) != 0)
+    dy = rnd(n, seed=2).to(dev)
+    y.backward(dy)
+    want_dx = torch.where(keep, dy * np.float32(1.0 / (1.0 - rate)), torch.zeros_like(dy))
+    assert torch.allclose(x.grad, want_dx, rtol=1e-6, atol=0)
+
+
+def test_clipped_bce_matches_keras_probability_path(dev):
+    """Keras binary_crossentropy without cached logits: clip to [1e-7, 1-1e-7], mean over the batch, gradient 0 where clipped."""
+    from handyrec_b200.autograd_ops import ClippedBCEFn
+
+    g = torch.Generator().manual_seed(0)
+    p = torch.rand(5000, 1, generator=g)
+    p[:5] = torch.tensor([[0.0], [1.0], [1e-9], [1 - 1e-9], [0.5]])
+    y = (torch.rand(5000, 1, generator=g) < 0.3).float()
+    pl = p.clone().requires_grad_(True)
+    # Keras clips in fp32 with fp32 constants (1 - 1e-7 rounds to 1 - 1.19e-7); the sums are taken in float64 here
+    pc = torch.clamp(pl, float(np.float32(1e-7)), float(np.float32(1.0) - np.float32(1e-7)))
+    want = -(y * torch.log(pc.double()) + (1 - y) * torch.log1p(-pc.double())).mean()
+    want.backward()
+    pd = p.to(dev).requires_grad_(True)
+    got = ClippedBCEFn.apply(pd, y.to(dev))
+    assert abs(float(got.detach()) - float(want.detach())) < 1e-5 * max(1.0, abs(float(want.detach())))
+    got.backward()
+    inner = (p > 1e-6) & (p < 1 - 1e-6)
+    close(pd.grad[inner], pl.grad[inner].float(), GRAD_TOL)
+    assert float(pd.grad[0]) == 0.0 and float(pd.grad[1]) == 0.0

@@ -1,14 +1,15 @@
 #!/usr/bin/env python
-"""bench.py -- DeepFM train samples/s on synthetic Criteo-shape data (BASELINE.json configs[2]).
+"""bench.py -- HandyRec hot path on B200: train samples/s on synthetic data of the shapes BASELINE.json names.
 
-    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
-    python bench.py --impl reference --steps K --warmup W    # the reference restated on CPU (oracle)
+    python bench.py --gpus N --steps K --warmup W                 # DeepFM Criteo-shape (configs[2]), this repo's CUDA path
+    python bench.py --workload din | retrieval                    # configs[1] (DIN, MovieLens-shaped) / configs[4] (YouTubeDNN, 10 M items)
+    python bench.py --impl reference --steps K --warmup W         # the reference restated on CPU (oracle), same workload
+    python -m torch.distributed.run ... bench.py --gpus N --verify   # N>1: correctness of the sharded step against a 1-GPU engine
 
-One "step" = one full DeepFM training step (lookup+pool, FM, DNN forward, BCE, backward, sorted-segment
-embedding update, dense optimiser) on one batch of 65536 synthetic samples (26 sparse + 13 dense, D=16).
-Prints ONE JSON line (contract in the task statement): `value` = device-resident throughput, `e2e` =
-through the host-facing API with pinned host buffers (H2D + D2H inside the timed region), `roofline` for the
-dominant kernel, `roofline_lookup` for the embedding lookup (the north-star kernel), `cpu_baseline`.
+One "step" = one full training step on one batch of synthetic samples.  Prints ONE JSON line (contract in the task statement):
+`value` = device-resident throughput (CUDA events), `e2e` = through the reference-shaped API -- `handyrec_b200.models.<Model>(...)
+.compile(...).fit(dict of host arrays)` -- with host batches packed, copied to the device and the loss read back inside the timed
+region, `roofline` for the dominant kernel, `roofline_lookup` / `roofline_embedding_bwd` for the north-star kernels, `cpu_baseline`.
 Nothing here reads /root/reference.
 """
 from __future__ import annotations
@@ -25,13 +26,14 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-# Criteo-like vocabulary vector (SURVEY.md §8d), +1 so that id 0 exists everywhere
+# Criteo-like vocabulary vector (SURVEY.md 8d), +1 so that id 0 exists everywhere
 CRITEO_VOCABS = [40_000_000, 40_000_000, 10_000_000, 5_000_000, 3_000_000, 2_000_000, 1_000_000, 500_000, 300_000, 100_000,
                  50_000, 20_000, 12_000, 10_000, 7_000, 5_000, 2_000, 1_500, 1_000, 600, 300, 100, 30, 20, 10, 4]
 CRITEO_VOCABS = [v + 1 for v in CRITEO_VOCABS]
 N_DENSE, EMB_DIM, BATCH = 13, 16, 65536
 DNN_HIDDEN = (256, 128, 1)
-LOOKUP_BYTES_PER_SAMPLE = len(CRITEO_VOCABS) * (4 + EMB_DIM * 4 + EMB_DIM * 4)  # ids + rows + output = 3432 (SURVEY §8d)
+LOOKUP_BYTES_PER_SAMPLE = len(CRITEO_VOCABS) * (4 + EMB_DIM * 4 + EMB_DIM * 4)  # ids + rows + output = 3432 (SURVEY 8d)
+CPU_VOCAB_CAP = 2_000_000  # rows per table on the CPU arm (dense Keras Adam over all 102 M rows would take minutes per step)
 
 
 def load_peaks():
@@ -40,6 +42,19 @@ def load_peaks():
         d = json.load(open(p))
         return {"hbm_gbs": float(d["hbm_gbs"]), "bf16_tflops": float(d["bf16_tflops"]), "bf16_tflops_sustained": float(d.get("bf16_tflops_sustained", d["bf16_tflops"])), "source": "measured"}
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+def load_traffic(kernel_key: str):
+    """DRAM bytes per launch of a kernel as parsed from this round's `ncu --set full` capture (profiles/summarize.py writes
+    profiles/r02_ncu_full.json); None when no capture is committed -- never a hand-typed number."""
+    p = os.path.join(ROOT, "profiles", "r02_ncu_full.json")
+    if not os.path.exists(p):
+        return None, None
+    rows = [r for r in json.load(open(p)).get("kernels", []) if kernel_key in r.get("name", "")]
+    if not rows:
+        return None, None
+    tot = sum(r["dram_read_bytes"] + r["dram_write_bytes"] for r in rows) / len(rows)
+    return tot, f"mean dram read+write per launch over {len(rows)} launches of {kernel_key} in profiles/r02_ncu_full.json"
 
 
 class ClockSampler:
@@ -88,13 +103,10 @@ class ClockSampler:
 # -------------------------------------------------------------------------------------------------
 # CPU restatement of one training step (oracle) -- used by cpu_baseline and by --impl reference
 # -------------------------------------------------------------------------------------------------
-def cpu_reference_arm(batch: int, vocab_cap: int, steps: int, warmup: int, seed: int = 1234):
-    """Time the op-for-op CPU restatement (oracle/) of the same DeepFM step on a bounded sample.
-
-    Same model (26 tables D=16, 13 dense, DNN [429,256,128,1], FM, BCE, Adam), embeddings looked up once
-    per feature group exactly like the reference (DeepFM.py:62-63), dense-table gradients + dense Adam like
-    Keras.  Vocabularies are capped at `vocab_cap` rows so that the dense Adam state fits and a step stays bounded.
-    """
+def cpu_deepfm_arm(batch: int, vocab_cap: int, steps: int, warmup: int, seed: int = 1234):
+    """Time the op-for-op CPU restatement (oracle/) of the same DeepFM step: 26 tables D=16, 13 dense, DNN [429,256,128,1], FM,
+    BCE, dense Adam on every table like Keras; embeddings looked up once per feature group exactly like the reference
+    (DeepFM.py:62-63).  Vocabularies are capped at `vocab_cap` rows so that the dense Adam state fits and a step stays bounded."""
     import torch
 
     import oracle
@@ -133,22 +145,35 @@ def cpu_reference_arm(batch: int, vocab_cap: int, steps: int, warmup: int, seed:
         step()
     dt = time.perf_counter() - t0
     return {"samples_per_s": batch * steps / dt, "ms_per_step": dt / steps * 1e3, "cores": torch.get_num_threads(),
-            "sample": f"{steps} steps of batch {batch}, vocab capped at {vocab_cap} rows/table, Adam, torch-CPU op-for-op restatement (TF unavailable in image)"}
+            "sample": f"{steps} steps of batch {batch}, every vocabulary capped at {vocab_cap} rows (dense Keras-style Adam over all rows of all tables), "
+                      "torch-CPU op-for-op restatement of the reference layers (TensorFlow is not in the image)"}
 
 
-WORKLOAD = "DeepFM Criteo-shape: 26 sparse + 13 dense, emb dim 16, DNN 429-256-128-1, batch 65536/GPU (BASELINE.json configs[2])"
+WORKLOADS = {
+    "deepfm": f"DeepFM Criteo-shape: 26 sparse + 13 dense, emb dim 16, DNN 429-256-128-1, batch 65536/GPU (BASELINE.json configs[2]); the CPU arm caps every vocabulary at {CPU_VOCAB_CAP} rows",
+    "din": "DIN MovieLens-1M-shaped: history seq len 50, emb dim 32, batch 4096, LAU (32,1) dice, DNN (64,32,1) dice (BASELINE.json configs[1])",
+    "retrieval": "YouTubeMatchDNN retrieval: 10 M-item catalogue, history L=50 mean-pooled, emb dim 32, genres L=6 D=8, batch 4096, 100 sampled (BASELINE.json configs[4])",
+}
+METRICS = {"deepfm": "DeepFM train samples/s", "din": "DIN train samples/s", "retrieval": "YouTubeMatchDNN train samples/s"}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    r = cpu_reference_arm(batch=8192, vocab_cap=200_000, steps=args.steps, warmup=args.warmup)
+    if args.workload == "deepfm":
+        r = cpu_deepfm_arm(batch=args.batch or BATCH, vocab_cap=CPU_VOCAB_CAP, steps=args.steps, warmup=args.warmup)
+        gb = args.batch or BATCH
+    else:
+        import bench_models
+
+        r = bench_models.cpu_arm(args.workload, steps=args.steps, warmup=args.warmup)
+        gb = r["batch"]
     line = {
-        "impl": "reference", "metric": "DeepFM train samples/s", "value": r["samples_per_s"], "unit": "samples/s", "n_gpus": args.gpus,
+        "impl": "reference", "metric": METRICS[args.workload], "value": r["samples_per_s"], "unit": "samples/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "global_batch": 8192,
+        "config": {"workload": WORKLOADS[args.workload], "global_batch": gb,
                    "reference_sample": "CPU restatement of the reference (oracle/) on a bounded sample of the workload: " + r["sample"]},
         "cpu_baseline": {"value": r["samples_per_s"], "unit": "samples/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]},
         "e2e": {"value": r["samples_per_s"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -158,29 +183,50 @@ def run_reference(args):
 
 
 # -------------------------------------------------------------------------------------------------
+def build_deepfm_model(vocabs):
+    """The reference-shaped construction: feature definitions -> feature groups -> DeepFM(...) -> compile (DeepFM.py / README)."""
+    from handyrec_b200 import keras_lite as KL
+    from handyrec_b200.features import DenseFeature, FeatureGroup, FeaturePool, SparseFeature
+    from handyrec_b200.models import DeepFM
+
+    sparse = [SparseFeature(f"C{i + 1}", v, EMB_DIM) for i, v in enumerate(vocabs)]
+    dense = [DenseFeature(f"I{i + 1}") for i in range(N_DENSE)]
+    pool = FeaturePool()
+    fm_group = FeatureGroup("fm", sparse, pool, l2_embd=0.0)
+    dnn_group = FeatureGroup("dnn", dense + sparse, pool, l2_embd=0.0)
+    model = DeepFM(fm_group, dnn_group, dnn_hidden_units=DNN_HIDDEN, dnn_activation="relu")
+    return model, KL
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="deepfm", choices=list(WORKLOADS))
     ap.add_argument("--optimizer", default="adam", choices=["adam", "sgd"])
     ap.add_argument("--ids", default="uniform", choices=["uniform", "zipf"])
-    ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--batch", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-peer-lookup", action="store_true", help="N>1: forward through the all-to-all row exchange instead of NVLink peer loads")
     ap.add_argument("--small-table-rows", type=int, default=131072,
                     help="tables up to this many rows take the dense (Keras-exact) optimiser step; at N>1 they are replicated instead of sharded (0 = off)")
+    ap.add_argument("--large-table-rows", type=int, default=0, help="C4: give every table above --small-table-rows this many rows (e.g. 100000000 at --gpus 8)")
     ap.add_argument("--scale-vocab", type=float, default=1.0, help="shrink every vocabulary (debug only; reported in config)")
+    ap.add_argument("--verify", action="store_true", help="N>1: 3 sharded steps at a small batch compared with a single-GPU engine on the concatenated batch")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if args.workload != "deepfm":
+        import bench_models
+
+        return bench_models.run(args, load_peaks, ClockSampler, WORKLOADS, METRICS)
 
     import torch
 
-    from handyrec_b200 import _lib
     from handyrec_b200 import kernels as K
-    from handyrec_b200.engine import DeepFMEngine, launch_count
+    from handyrec_b200.engine import launch_count
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -191,23 +237,30 @@ def main():
         import torch.distributed as dist
 
         dist.init_process_group("nccl", device_id=dev)
+    if args.verify:
+        import bench_models
+
+        return bench_models.verify_sharded(args, CRITEO_VOCABS, N_DENSE, EMB_DIM)
     peaks = load_peaks()
 
     # ---- workload -------------------------------------------------------------------------------
-    B = args.batch
+    B = args.batch or BATCH
     vocabs = [max(4, int(v * args.scale_vocab)) for v in CRITEO_VOCABS]
-    tables = []
+    if args.large_table_rows:
+        vocabs = [args.large_table_rows if v > args.small_table_rows else v for v in vocabs]
     fields = [(f, 1, "none") for f in range(len(vocabs))]
+    model = None
     if world == 1:
-        for f, v in enumerate(vocabs):
-            t = torch.empty(v, EMB_DIM, device=dev)
-            K.init_uniform(t, seed=7 + f)
-            tables.append(t)
-        eng = DeepFMEngine(tables, fields, N_DENSE, DNN_HIDDEN, "relu", batch_size=B, optimizer=args.optimizer, lr=1e-3, l2_embd=0.0, seed=2022,
-                           dense_table_max_rows=args.small_table_rows)
+        # the reference-shaped call chain: feature groups -> DeepFM(...) -> compile; compile() lowers the graph onto the fused engine
+        model, KL = build_deepfm_model(vocabs)
+        model.dense_table_max_rows = args.small_table_rows
+        model.compile(optimizer=KL.Adam(learning_rate=1e-3) if args.optimizer == "adam" else KL.SGD(learning_rate=1e-3), loss=KL.binary_crossentropy)
+        assert model._fused is not None, "the DeepFM graph was not lowered onto the fused engine"
+        model._fused.build(B, model.optimizer)
+        eng = model._fused.engine
     else:
         # row-sharded tables: this rank holds rows r with r % world == rank (bit-identical to the rows of the full table)
-        from handyrec_b200.sharded import ShardedDeepFMEngine, TorchDistComm, shard_rows
+        from handyrec_b200.sharded import ShardedDeepFMEngine, TorchDistComm
 
         comm = TorchDistComm()
         # shards live in symmetric memory (peers map them over NVLink); small tables are replicated in full on every rank
@@ -246,7 +299,7 @@ def main():
         torch.cuda.synchronize()
 
     # ---- device-resident timed region -----------------------------------------------------------
-    for s in range(args.warmup):
+    for s in range(max(args.warmup, 8 if eng.autotune_embedding_bwd else 0)):  # the engine picks its backward algorithm in steps 3-6
         eng.train_step_on_device(ids_pool[s % NB], dense_pool[s % NB], label_pool[s % NB])
     barrier()
     l0 = launch_count()
@@ -262,22 +315,54 @@ def main():
     ms = e0.elapsed_time(e1)
     launches = launch_count() - l0
 
-    # ---- end-to-end through the host-facing API (pinned host buffers, H2D + D2H inside) ----------
-    # (a) the fit-like API: inputs prefetched on a copy stream, losses copied back asynchronously every step
-    eng.fit_batches(host[s % NB] for s in range(3))
-    barrier()
-    t0 = time.perf_counter()
-    losses = eng.fit_batches(host[s % NB] for s in range(args.steps))
-    torch.cuda.synchronize()
-    e2e_ms = (time.perf_counter() - t0) * 1e3
-    loss = losses[-1]
-    # (b) one blocking train_on_batch call per step (H2D, step, D2H loss, host wait), for comparison
-    barrier()
-    t0 = time.perf_counter()
-    for s in range(args.steps):
-        eng.train_on_batch(*host[s % NB])
-    torch.cuda.synchronize()
-    e2e_sync_ms = (time.perf_counter() - t0) * 1e3
+    # ---- end-to-end through the reference-shaped API ----------------------------------------------
+    if model is not None:
+        # (a) Model.fit on a dict of per-feature host arrays (what Keras takes): steps x B samples; per step the host packs the
+        # batch (hrb_host_pack_*, background thread), copies it to the device on a copy stream and reads the loss back
+        import numpy as np
+
+        n_fit = args.steps * B
+        x_host, reps = {}, (args.steps + NB - 1) // NB
+        ids_np = np.concatenate([h[0].numpy() for h in host] * reps)[:n_fit]
+        dense_np = np.concatenate([h[1].numpy() for h in host] * reps)[:n_fit]
+        y_host = np.concatenate([h[2].numpy() for h in host] * reps)[:n_fit]
+        for f in range(len(vocabs)):
+            x_host[f"C{f + 1}"] = np.ascontiguousarray(ids_np[:, f : f + 1])
+        for j in range(N_DENSE):
+            x_host[f"I{j + 1}"] = np.ascontiguousarray(dense_np[:, j : j + 1])
+        small = {k: v[: 3 * B] for k, v in x_host.items()}
+        model.fit(small, y_host[: 3 * B], batch_size=B, epochs=1)  # warm-up of the fit path (pinned slots, copy stream)
+        barrier()
+        t0 = time.perf_counter()
+        hist = model.fit(x_host, y_host, batch_size=B, epochs=1)
+        torch.cuda.synchronize()
+        e2e_ms = (time.perf_counter() - t0) * 1e3
+        loss = float(model.last_losses[-1])
+        e2e_api = "handyrec_b200.models.DeepFM(...).compile(Adam, binary_crossentropy).fit(dict of 39 per-feature host arrays, batch_size=65536): host packing, H2D and loss D2H every step inside the timed region"
+        # (b) one blocking train_on_batch call per step through the same Model, for comparison
+        xb = {k: v[:B] for k, v in x_host.items()}
+        model.train_on_batch(xb, y_host[:B])
+        barrier()
+        t0 = time.perf_counter()
+        for s in range(args.steps):
+            model.train_on_batch(xb, y_host[:B])
+        torch.cuda.synchronize()
+        e2e_sync_ms = (time.perf_counter() - t0) * 1e3
+    else:
+        eng.fit_batches(host[s % NB] for s in range(3))
+        barrier()
+        t0 = time.perf_counter()
+        losses = eng.fit_batches(host[s % NB] for s in range(args.steps))
+        torch.cuda.synchronize()
+        e2e_ms = (time.perf_counter() - t0) * 1e3
+        loss = losses[-1]
+        e2e_api = "ShardedDeepFMEngine.fit_batches (pinned host batches, prefetching copy stream, async loss read-back every step)"
+        barrier()
+        t0 = time.perf_counter()
+        for s in range(args.steps):
+            eng.train_on_batch(*host[s % NB])
+        torch.cuda.synchronize()
+        e2e_sync_ms = (time.perf_counter() - t0) * 1e3
     clk = clocks.stop()
 
     if world > 1:
@@ -315,7 +400,6 @@ def main():
         return
     step_ms = ms / args.steps
     total_phase = sum(phases.values())
-    dom = max(phases, key=phases.get)
     flops = {}
     units = eng.units
     Ks = [eng.K0] + units[:-1]
@@ -331,21 +415,25 @@ def main():
     gemm_ms = sum(phases[k] for k in gemm_names)
     gemm_flops = sum(flops[k] for k in gemm_names)
     ach = gemm_flops / (gemm_ms * 1e-3) / 1e12
-    roofline = {"kernel": "tc::gemm_tc_kernel (tcgen05 3xTF32, %d launches/step; bwd_w phases include their split-reduce/colsum kernels)" % len(gemm_names),
+    full_batch = B == BATCH and args.scale_vocab == 1.0
+    g_traffic, g_note = load_traffic("gemm_tc_kernel") if full_batch else (None, None)
+    roofline = {"kernel": "tc::gemm_tc_kernel (tcgen05 3xTF32, %d launches/step; bwd_w phases include their split-reduce kernels)" % len(gemm_names),
                 "bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": ach / peaks["bf16_tflops_sustained"],
-                "traffic": 182.1e6 if B == BATCH else None, "traffic_note": "dram read+write per launch, mean of the step's 9 GEMM launches in profiles/r01_ncu_full_summary.md (1639 MB per step, captured before the transposed activation stores were dropped)",
+                "traffic": g_traffic, "traffic_note": g_note,
                 "share_of_step": gemm_ms / total_phase, "flops_per_step": gemm_flops,
                 "peak_source": f"{peaks['source']} bf16 sustained (kernel timed inside a long step)",
-                "note": "fp32 parity needs 3 TF32 MMAs per product at half the bf16 rate: ceiling of this scheme = 1/6 = 0.167 of the bf16 peak (DESIGN.md 3); ncu tensor-pipe active 58-80% on the large GEMMs (profiles/r01_ncu_full_summary.md)"}
+                "note": "fp32 parity needs 3 TF32 MMAs per product at half the bf16 rate: ceiling of this scheme = 1/6 = 0.167 of the bf16 peak (DESIGN.md 3)"}
     lk = "lookup_fm_fwd" if (world == 1 or eng.peer_lookup) else "sharded_lookup_fwd"
     lk_ach = lookup_bytes / (phases[lk] * 1e-3) / 1e9
     peer = world > 1 and eng.peer_lookup
     n_small = sum(1 for v in vocabs if v <= args.small_table_rows)
     n_sharded = len(vocabs) - n_small
+    l_traffic, l_note = load_traffic("lookup_tile_kernel") if (full_batch and world == 1) else (None, None)
     rl_lookup = {"kernel": "hrb::lookup_tile_kernel (fused lookup + FM)" if world == 1 else
                  ("hrb::lookup_tile_kernel reading row-sharded tables over NVLink peer mappings" if peer else "row exchange (route + all-to-all + gather + scatter)"),
                  "bound": "hbm", "achieved": lk_ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": lk_ach / peaks["hbm_gbs"],
-                 "traffic": 163.7e6 if (world == 1 and B == BATCH) else None, "nvlink_bytes_per_step": None if world == 1 else B * n_sharded * EMB_DIM * 4 * (world - 1) / world, "traffic_note": "dram read+write per launch from profiles/r01_ncu_full_summary.md",
+                 "traffic": l_traffic, "traffic_note": l_note,
+                 "nvlink_bytes_per_step_algorithmic": None if world == 1 else B * n_sharded * EMB_DIM * 4 * (world - 1) / world,
                  "peak_source": f"{peaks['source']} copy bandwidth", "bytes_per_sample": LOOKUP_BYTES_PER_SAMPLE, "in_step_ms": phases[lk],
                  "alone_ms": lookup_alone_ms, "alone_achieved": lookup_bytes / (lookup_alone_ms * 1e-3) / 1e9,
                  "alone_frac": lookup_bytes / (lookup_alone_ms * 1e-3) / 1e9 / peaks["hbm_gbs"]}
@@ -355,25 +443,30 @@ def main():
     eb_bytes = B * len(vocabs) * (4 + EMB_DIM * 4) + uniq * EMB_DIM * 4 * 2 * S
     eb_ms = phases.get(eb, 0.0) + phases.get("replicated_embedding_bwd", 0.0)
     eb_ach = eb_bytes / (eb_ms * 1e-3) / 1e9
-    rl_emb = {"kernel": "bwd_keys + radix sort + bwd_chunk/hot/merge (a13)", "bound": "hbm", "achieved": eb_ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-              "frac": eb_ach / peaks["hbm_gbs"], "unique_rows": uniq, "bytes_per_step": eb_bytes, "in_step_ms": eb_ms}
+    b_traffic, b_note = load_traffic("bwd_unit_kernel") if (full_batch and world == 1) else (None, None)
+    rl_emb = {"kernel": "a13: bwd_prep + split_count/scan/scatter + bwd_unit_kernel (two-level radix partition fused with the row update)"
+              if getattr(eng, "bwd_algo", "auto") != "sort" else "a13: bwd_keys + radix sort + bwd_chunk/hot/merge",
+              "algo": getattr(eng, "bwd_algo", "auto"), "algo_trial_ms": getattr(eng, "bwd_algo_ms", None),
+              "bound": "hbm", "achieved": eb_ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+              "frac": eb_ach / peaks["hbm_gbs"], "unique_rows": uniq, "bytes_per_step": eb_bytes, "in_step_ms": eb_ms,
+              "traffic": b_traffic, "traffic_note": b_note}
 
     cpu = None
     if not args.no_cpu_baseline:
-        r = cpu_reference_arm(batch=8192, vocab_cap=200_000, steps=3, warmup=1)
+        r = cpu_deepfm_arm(batch=B, vocab_cap=CPU_VOCAB_CAP, steps=3, warmup=1)
         cpu = {"value": r["samples_per_s"], "unit": "samples/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]}
 
     line = {
-        "metric": "DeepFM train samples/s", "value": B * world * args.steps / (ms * 1e-3), "unit": "samples/s", "n_gpus": world,
+        "metric": METRICS["deepfm"], "value": B * world * args.steps / (ms * 1e-3), "unit": "samples/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD,
+        "config": {"workload": WORKLOADS["deepfm"],
                    "global_batch": B * world, "tables_rows": sum(vocabs), "tables_gb": sum(vocabs) * EMB_DIM * 4 / 1e9, "ids": args.ids,
                    "optimizer": f"{args.optimizer} (dense params and the {n_small} tables of <= {args.small_table_rows} rows, Keras-exact dense step) + {eng.emb_opt} (touched rows of the {n_sharded} large tables)", "l2_embd": 0.0,
-                   "l2_flush": "inputs larger than L2 (6.5 GB of tables, rotating pool of 4 batches)", "scale_vocab": args.scale_vocab,
+                   "l2_flush": "inputs larger than L2 (%.1f GB of tables, rotating pool of 4 batches)" % (sum(vocabs) * EMB_DIM * 4 / 1e9), "scale_vocab": args.scale_vocab,
                    "parallelism": "single GPU" if world == 1 else f"dp{world}: batch split, {n_sharded} large tables row-sharded (row % {world}), {n_small} small tables replicated (gradients all-reduced with the dense ones), forward = fused lookup+FM reading peer shards over NVLink (symmetric memory), backward = NCCL all-to-all of gradient rows to the owners, all-reduce for dense grads"},
         "e2e": {"value": B * world * args.steps / (e2e_ms * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": eng.h2d_bytes_per_step(B), "d2h_bytes_per_step": 4,
-                "ms_per_step": e2e_ms / args.steps, "last_loss": loss, "api": "DeepFMEngine.fit_batches (pinned host batches, prefetching copy stream, async loss read-back every step)",
+                "ms_per_step": e2e_ms / args.steps, "last_loss": loss, "api": e2e_api,
                 "blocking_train_on_batch_samples_per_s": B * world * args.steps / (e2e_sync_ms * 1e-3)},
         "gpu_launches": launches, "gpu_launches_per_step": launches / max(args.steps, 1),
         "clocks": clk, "roofline": roofline, "roofline_lookup": rl_lookup, "roofline_embedding_bwd": rl_emb, "cpu_baseline": cpu,

@@ -19,10 +19,11 @@ class EmbeddingFn(torch.autograd.Function):
     """layers/tools.py:87-101 forward; TF IndexedSlices gradient as a dense, sorted-segment reduction."""
 
     @staticmethod
-    def forward(ctx, table, ids, mask_zero):
+    def forward(ctx, table, ids, mask_zero, sparse_sink=None):
         out, mask = K.embedding_fwd(table, ids.contiguous(), mask_zero)
         ctx.save_for_backward(ids)
         ctx.vocab = table.shape[0]
+        ctx.sink = sparse_sink
         ctx.mark_non_differentiable(*( [mask] if mask is not None else []))
         return (out, mask) if mask is not None else (out, torch.empty(0, device=table.device, dtype=torch.bool))
 
@@ -30,7 +31,12 @@ class EmbeddingFn(torch.autograd.Function):
     def backward(ctx, dout, _dmask):
         (ids,) = ctx.saved_tensors
         D = dout.shape[-1]
-        return K.embedding_bwd_dense(ids.reshape(-1), dout.contiguous().reshape(-1, D), ctx.vocab), None, None
+        if ctx.sink is not None:
+            # a large table: keep the gradient as (ids, rows) -- TF's IndexedSlices -- for the sorted-segment row update
+            # (CustomEmbedding.apply_sparse) instead of materialising vocab x D floats per step
+            ctx.sink.append((ids.reshape(-1), dout.contiguous().reshape(-1, D)))
+            return None, None, None, None
+        return K.embedding_bwd_dense(ids.reshape(-1), dout.contiguous().reshape(-1, D), ctx.vocab), None, None, None
 
 
 class SeqPoolFn(torch.autograd.Function):
@@ -67,25 +73,48 @@ class FMFn(torch.autograd.Function):
         return dx, dw.reshape(w.shape), dw0
 
 
+TC_MIN_ROWS = 4096  # layer-face Dense: from this many rows on the GEMMs run on the tcgen05 3xTF32 kernel (DIN's LAU MLP: B*T rows)
+
+
+def _tc_shape(M: int, Kd: int, N: int) -> bool:
+    return M >= TC_MIN_ROWS and Kd >= 16 and N >= 16 and Kd % 4 == 0 and N % 4 == 0
+
+
 class DenseFn(torch.autograd.Function):
-    """Keras Dense on the last axis with a fused element-wise activation (layers/core.py:61-69)."""
+    """Keras Dense on the last axis with a fused element-wise activation (layers/core.py:61-69).
+
+    Tall inputs -- the local-activation MLP of DIN sees B*T = 204 800 rows (sequence.py:99), the towers B -- take the tensor-core
+    kernel (error-compensated 3xTF32 with fp32 accumulation, same parity as the FFMA kernel): forward on W^T, backward dx in the
+    TN form as stored, dW as a split-K product that reads x untransposed; only dz^T (N x M) is materialised for it.  Everything
+    else stays on the FFMA kernel."""
 
     @staticmethod
     def forward(ctx, x, w, b, act):
         lead = x.shape[:-1]
         x2 = x.contiguous().reshape(-1, x.shape[-1])
-        y = K.dense_fwd(x2, w.contiguous(), b, act)
+        w = w.contiguous()
+        M, Kd = x2.shape
+        N = w.shape[1]
+        ctx.tc = _tc_shape(M, Kd, N) and act in (None, "linear", "relu", "sigmoid", "tanh")
+        if ctx.tc:
+            y = K.dense_fwd_t(x2, K.transpose(w), b, act)
+        else:
+            y = K.dense_fwd(x2, w, b, act)
         ctx.save_for_backward(x2, w, y)
         ctx.act, ctx.lead, ctx.has_bias = act, lead, b is not None
-        return y.reshape(*lead, w.shape[1])
+        return y.reshape(*lead, N)
 
     @staticmethod
     def backward(ctx, dy):
         x2, w, y = ctx.saved_tensors
         dy2 = dy.contiguous().reshape(-1, w.shape[1])
         dz = K.act_bwd(y, dy2, ctx.act) if ctx.act not in (None, "linear") else dy2
-        dx = K.dense_bwd_x(dz, w.contiguous())
-        dw, db = K.dense_bwd_w(x2, dz, want_bias=ctx.has_bias)
+        if ctx.tc:
+            dx = K.dense_bwd_x_t(dz, w)
+            dw, db = K.dense_bwd_w_xn(x2, K.transpose(dz), want_bias=ctx.has_bias)
+        else:
+            dx = K.dense_bwd_x(dz, w)
+            dw, db = K.dense_bwd_w(x2, dz, want_bias=ctx.has_bias)
         return dx.reshape(*ctx.lead, w.shape[0]), dw, (db if ctx.has_bias else None), None
 
 
@@ -278,3 +307,97 @@ class ActivationFn(torch.autograd.Function):
     def backward(ctx, dy):
         (y,) = ctx.saved_tensors
         return K.act_bwd(y, dy.contiguous().reshape(-1, 1), ctx.act).reshape(dy.shape), None
+
+
+# ---------------------------------------------------------------------------------------------
+# (f1) retrieval loss pieces: SampledSoftmaxLayer (layers/tools.py:32-84), DSSM cosine scaling (DSSM.py:105-106)
+# ---------------------------------------------------------------------------------------------
+class MatmulNTFn(torch.autograd.Function):
+    """a (M,K) @ b (N,K)^T -> (M,N): the sampled logits `inputs @ sampled_w^T`.  The three products are the dense layer's GEMMs
+    with the roles swapped (hrb_dense_bwd_x computes A.B^T, hrb_dense_fwd A.B, hrb_dense_bwd_w A^T.B)."""
+
+    @staticmethod
+    def forward(ctx, a, b):
+        a, b = a.contiguous(), b.contiguous()
+        ctx.save_for_backward(a, b)
+        return K.dense_bwd_x(a, b, mode=_lib.GEMM_FP32)
+
+    @staticmethod
+    def backward(ctx, g):
+        a, b = ctx.saved_tensors
+        g = g.contiguous()
+        da = K.dense_fwd(g, b, None, None, mode=_lib.GEMM_FP32)                 # (M,N) @ (N,K)
+        db, _ = K.dense_bwd_w(g, a, want_bias=False, mode=_lib.GEMM_FP32)       # (M,N)^T @ (M,K) -> (N,K)
+        return da, db
+
+
+class RowDotFn(torch.autograd.Function):
+    """out[m] = <a[m,:], b[m,:]>: the true-class logits."""
+
+    @staticmethod
+    def forward(ctx, a, b):
+        a, b = a.contiguous(), b.contiguous()
+        M, Kd = a.shape
+        out = torch.empty(M, device=a.device, dtype=torch.float32)
+        call("hrb_rowdot", K._p(a), Kd, K._p(b), Kd, M, Kd, K._p(out), K._stream())
+        ctx.save_for_backward(a, b)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        a, b = ctx.saved_tensors
+        g = g.contiguous()
+        M, Kd = a.shape
+        da, db = torch.empty_like(a), torch.empty_like(b)
+        call("hrb_rowscale", K._p(b), Kd, K._p(g), M, Kd, K._p(da), Kd, K._stream())
+        call("hrb_rowscale", K._p(a), Kd, K._p(g), M, Kd, K._p(db), Kd, K._stream())
+        return da, db
+
+
+class SampledSoftmaxFn(torch.autograd.Function):
+    """- log Q, accidental-hit mask and softmax cross-entropy against the true class, fused (hrb_sampled_softmax)."""
+
+    @staticmethod
+    def forward(ctx, true_logit, sampled_logit, labels, sampled, true_expected, sampled_expected, num_tries, range_max, remove_hits):
+        true_logit, sampled_logit = true_logit.contiguous(), sampled_logit.contiguous()
+        B, S = sampled_logit.shape
+        loss = torch.empty(B, device=true_logit.device, dtype=torch.float32)
+        ctx.save_for_backward(true_logit, sampled_logit, labels, sampled, true_expected, sampled_expected)
+        ctx.cfg = (float(num_tries), int(range_max), int(bool(remove_hits)))
+        call("hrb_sampled_softmax", K._p(true_logit), K._p(sampled_logit), S, K._p(labels), K._p(sampled), B, S, K._p(true_expected),
+             K._p(sampled_expected), float(num_tries), int(range_max), int(bool(remove_hits)), None, K._p(loss), None, None, K._stream())
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        true_logit, sampled_logit, labels, sampled, te, se = ctx.saved_tensors
+        nt, rm, rh = ctx.cfg
+        B, S = sampled_logit.shape
+        g = g.contiguous()
+        dt, ds = torch.empty_like(true_logit), torch.empty_like(sampled_logit)
+        call("hrb_sampled_softmax", K._p(true_logit), K._p(sampled_logit), S, K._p(labels), K._p(sampled), B, S, K._p(te), K._p(se), nt, rm, rh,
+             K._p(g), None, K._p(dt), K._p(ds), K._stream())
+        return dt, ds, None, None, None, None, None, None, None
+
+
+class L2NormalizeFn(torch.autograd.Function):
+    """tf.nn.l2_normalize(x) over the WHOLE tensor (no axis), as DSSM.py:105-106 calls it."""
+
+    @staticmethod
+    def forward(ctx, x, eps):
+        x = x.contiguous()
+        y = torch.empty_like(x)
+        stat = torch.empty(1, device=x.device, dtype=torch.float32)
+        scratch = torch.empty(256, device=x.device, dtype=torch.float32)
+        call("hrb_l2_normalize_fwd", K._p(x), x.numel(), float(eps), K._p(y), K._p(stat), K._p(scratch), K._stream())
+        ctx.save_for_backward(y, stat)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        y, stat = ctx.saved_tensors
+        dy = dy.contiguous()
+        dx = torch.empty_like(dy)
+        scratch = torch.empty(256, device=dy.device, dtype=torch.float32)
+        call("hrb_l2_normalize_bwd", K._p(y), K._p(dy), dy.numel(), K._p(stat), K._p(dx), K._p(scratch), K._stream())
+        return dx, None

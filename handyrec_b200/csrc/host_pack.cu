@@ -1,0 +1,143 @@
+// host_pack.cu -- host-side input glue of the drop-in face (no device code): FeatureGroup.construct_inputs hands Keras one
+// array per feature (features/group.py:218-248: (N,1) ids, (N,seq_len) histories, (N,dim) dense values); the fused lookup
+// wants ONE packed int32 id matrix and ONE fp32 dense matrix per batch.  These two entry points gather the
+// rows [row_start, row_start+rows) of every column array into a (pinned) destination matrix with a small persistent thread
+// pool, so that Model.fit can assemble batch t+1 on the host while batch t trains on the GPU.
+#include <stdint.h>
+#include <string.h>
+
+#include <condition_variable>
+#include <functional>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+#include "common.cuh"
+
+namespace {
+
+class Pool {
+ public:
+  explicit Pool(int n) : stop_(false), pending_(0), gen_(0) {
+    for (int i = 0; i < n; ++i) workers_.emplace_back([this, i] { loop(i); });
+  }
+  ~Pool() {
+    {
+      std::lock_guard<std::mutex> l(mu_);
+      stop_ = true;
+    }
+    cv_.notify_all();
+    for (auto& t : workers_) t.join();
+  }
+  int size() const { return (int)workers_.size(); }
+  // run fn(worker) on workers [0, n) and wait
+  void run(int n, const std::function<void(int)>& fn) {
+    std::unique_lock<std::mutex> l(mu_);
+    fn_ = &fn;
+    active_ = n;
+    pending_ = n;
+    ++gen_;
+    cv_.notify_all();
+    done_.wait(l, [this] { return pending_ == 0; });
+  }
+
+ private:
+  void loop(int id) {
+    uint64_t seen = 0;
+    for (;;) {
+      const std::function<void(int)>* fn = nullptr;
+      {
+        std::unique_lock<std::mutex> l(mu_);
+        cv_.wait(l, [&] { return stop_ || gen_ != seen; });
+        if (stop_) return;
+        seen = gen_;
+        if (id >= active_) continue;
+        fn = fn_;
+      }
+      (*fn)(id);
+      {
+        std::lock_guard<std::mutex> l(mu_);
+        if (--pending_ == 0) done_.notify_all();
+      }
+    }
+  }
+  std::vector<std::thread> workers_;
+  std::mutex mu_;
+  std::condition_variable cv_, done_;
+  const std::function<void(int)>* fn_ = nullptr;
+  bool stop_;
+  int pending_, active_ = 0;
+  uint64_t gen_;
+};
+
+Pool& pool() {
+  static Pool p((int)std::max(1u, std::min(16u, std::thread::hardware_concurrency())));
+  return p;
+}
+std::mutex g_pack_mu;  // one packing job at a time (the pool is shared)
+
+template <typename D, typename S>
+inline void copy_block(const S* src, int64_t src_ld, int64_t width, int64_t r0, int64_t r1, D* dst, int64_t dst_ld) {
+  for (int64_t r = r0; r < r1; ++r) {
+    const S* s = src + r * src_ld;
+    D* d = dst + (r - r0) * dst_ld;
+    for (int64_t c = 0; c < width; ++c) d[c] = (D)s[c];
+  }
+}
+
+template <typename D>
+int pack(const void* const* cols, const int32_t* dtype, const int64_t* width, const int64_t* ld, int32_t n_cols, int64_t row_start,
+         int64_t rows, D* dst, int64_t dst_ld, int32_t n_threads) {
+  if (rows == 0) return HRB_OK;
+  std::lock_guard<std::mutex> job(g_pack_mu);
+  Pool& p = pool();
+  int nt = n_threads <= 0 ? p.size() : std::min(n_threads, p.size());
+  if (rows < 4096) nt = 1;
+  const int64_t per = (rows + nt - 1) / nt;
+  auto work = [&](int t) {
+    const int64_t a = row_start + t * per, b = std::min(row_start + rows, a + per);
+    if (a >= b) return;
+    int64_t col0 = 0;
+    for (int c = 0; c < n_cols; ++c) {
+      D* d = dst + (a - row_start) * dst_ld + col0;
+      switch (dtype[c]) {
+        case 0: copy_block(static_cast<const int32_t*>(cols[c]), ld[c], width[c], a, b, d, dst_ld); break;
+        case 1: copy_block(static_cast<const int64_t*>(cols[c]), ld[c], width[c], a, b, d, dst_ld); break;
+        case 2: copy_block(static_cast<const float*>(cols[c]), ld[c], width[c], a, b, d, dst_ld); break;
+        default: copy_block(static_cast<const double*>(cols[c]), ld[c], width[c], a, b, d, dst_ld); break;
+      }
+      col0 += width[c];
+    }
+  };
+  if (nt == 1) work(0); else p.run(nt, work);
+  return HRB_OK;
+}
+
+int check(const char* who, const void* const* cols, const int32_t* dtype, const int64_t* width, const int64_t* ld, int32_t n_cols,
+          int64_t row_start, int64_t rows, const void* dst, int64_t dst_ld) {
+  HRB_REQUIRE(n_cols >= 0 && rows >= 0 && row_start >= 0 && (rows == 0 || dst != nullptr), "%s: bad argument", who);
+  int64_t total = 0;
+  for (int c = 0; c < n_cols; ++c) {
+    HRB_REQUIRE(cols && dtype && width && ld && cols[c] != nullptr && width[c] > 0 && ld[c] >= width[c] && dtype[c] >= 0 && dtype[c] <= 3,
+                "%s: column %d is malformed", who, c);
+    total += width[c];
+  }
+  HRB_REQUIRE(dst_ld >= total, "%s: dst_ld %lld < %lld packed columns", who, (long long)dst_ld, (long long)total);
+  return HRB_OK;
+}
+
+}  // namespace
+
+HRB_API int hrb_host_pack_i32(const void* const* cols_host, const int32_t* dtype_host, const int64_t* width_host, const int64_t* ld_host,
+                              int32_t n_cols, int64_t row_start, int64_t rows, int32_t* dst_host, int64_t dst_ld, int32_t n_threads) {
+  int rc = check("hrb_host_pack_i32", cols_host, dtype_host, width_host, ld_host, n_cols, row_start, rows, dst_host, dst_ld);
+  if (rc != HRB_OK) return rc;
+  return pack<int32_t>(cols_host, dtype_host, width_host, ld_host, n_cols, row_start, rows, dst_host, dst_ld, n_threads);
+}
+
+HRB_API int hrb_host_pack_f32(const void* const* cols_host, const int32_t* dtype_host, const int64_t* width_host, const int64_t* ld_host,
+                              int32_t n_cols, int64_t row_start, int64_t rows, float* dst_host, int64_t dst_ld, int32_t n_threads) {
+  int rc = check("hrb_host_pack_f32", cols_host, dtype_host, width_host, ld_host, n_cols, row_start, rows, dst_host, dst_ld);
+  if (rc != HRB_OK) return rc;
+  return pack<float>(cols_host, dtype_host, width_host, ld_host, n_cols, row_start, rows, dst_host, dst_ld, n_threads);
+}

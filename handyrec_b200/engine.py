@@ -333,8 +333,9 @@ class DeepFMEngine:
     def _embedding_backward(self, ids, B, st, op) -> None:
         self._zero_table_grads()
         trial = None
-        if self.autotune_embedding_bwd and self._marks is None and B == self.B and 3 <= self.step_count <= 6:
-            trial = _lib.BWD_UNITS if self.step_count % 2 else _lib.BWD_SORT
+        n_trials = len(self._bwd_trials or [])
+        if self.autotune_embedding_bwd and self._marks is None and B == self.B and self.step_count >= 3 and n_trials < 4 and self.bwd_algo == "auto":
+            trial = _lib.BWD_UNITS if n_trials % 2 == 0 else _lib.BWD_SORT
             call("hrb_plan_set_bwd_algo", self.plan._h, trial)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
@@ -344,7 +345,7 @@ class DeepFMEngine:
             e1.record()
             e1.synchronize()
             self._bwd_trials = (self._bwd_trials or []) + [(trial, e0.elapsed_time(e1))]
-            if self.step_count == 6:
+            if len(self._bwd_trials) == 4:
                 best = {}
                 for algo, ms in self._bwd_trials:
                     best[algo] = min(best.get(algo, 1e30), ms)
@@ -541,16 +542,20 @@ class DeepFMEngine:
         pool: List[torch.Tensor] = []  # pinned read-back slots are carved from 256-float chunks (one pinned allocation per 256 steps)
 
         def upload(slot, batch):
-            ids_h, dense_h, label_h = batch
+            packed = batch if hasattr(batch, "views") else None  # lowering.HostBatch: a reusable pinned slot
+            ids_h, dense_h, label_h = packed.views() if packed is not None else batch
             B = ids_h.shape[0]
             with torch.cuda.stream(self._copy_stream):
                 self._copy_stream.wait_event(self._stage_free[slot])  # the previous user of this slot has finished
                 ids_d, dense_d, label_d = self._stage[slot]
-                ids_d[:B].copy_(ids_h, non_blocking=True)
+                ids_d[:B].copy_(ids_h[:, : self.ids_cols], non_blocking=True)
                 if self.n_dense:
-                    dense_d[:B].copy_(dense_h, non_blocking=True)
+                    dense_d[:B].copy_(dense_h[:, : self.n_dense], non_blocking=True)
                 label_d[:B].copy_(label_h, non_blocking=True)
                 self._stage_ready[slot].record(self._copy_stream)
+                if packed is not None:  # the producer may refill the pinned slot once these copies have left it
+                    packed.copied = torch.cuda.Event()
+                    packed.copied.record(self._copy_stream)
             return B
 
         for e in self._stage_free:

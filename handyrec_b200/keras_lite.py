@@ -63,6 +63,14 @@ class KTensor:
     def __add__(self, other):
         return Lambda(lambda a, b: a + b, lambda sa, sb: sa, name="add")([self, other])
 
+    def __mul__(self, other):
+        if isinstance(other, KTensor):
+            return Lambda(lambda a, b: a * b, lambda sa, sb: sa, name="multiply")([self, other])
+        c = float(other)
+        return Lambda(lambda a: a * c, lambda sa: sa, name="scale")(self)
+
+    __rmul__ = __mul__
+
     def __repr__(self):
         return f"<KTensor {self.name or ''} shape={self.shape} dtype={self.dtype}>"
 
@@ -212,6 +220,11 @@ def _init(initializer, shape):
     if name in ("ones", "one"):
         return torch.ones(shape)
     if name in ("uniform", "random_uniform", "randomuniform"):
+        n = 1
+        for d in shape:
+            n *= d
+        if n >= (1 << 22) and device().type == "cuda":  # large tables are drawn on the device (no multi-GB host tensor)
+            return torch.rand(shape, device=device()).sub_(0.5).mul_(0.1)
         return (torch.rand(shape) - 0.5) * 0.1  # Keras RandomUniform(-0.05, 0.05)
     if name in ("glorot_uniform", "glorotuniform"):
         fan_in, fan_out = (shape[0], shape[-1]) if len(shape) > 1 else (shape[0], shape[0])
@@ -396,6 +409,7 @@ class Model:
         return bound
 
     def __call__(self, x, training=False):
+        self.sync()
         feed = self._bind(x)
         vals: Dict[Tuple[int, int], torch.Tensor] = {}
 
@@ -412,7 +426,19 @@ class Model:
                 vals[(n.id, i)] = o
         return _map_structure(get, self.outputs)
 
+    # ---- fused execution (handyrec_b200.lowering) ----------------------------------------------------
+    _fused = None
+    fuse = True  # set to False before compile() to keep the layer-by-layer path (tests compare the two)
+
+    def sync(self) -> None:
+        """Make the layers' weights current after fused training steps (train_on_batch leaves them in the engine)."""
+        if self._fused is not None:
+            self._fused.sync_to_layers()
+
     def predict(self, x, batch_size=None):
+        if self._fused is not None and self._fused.engine is not None and isinstance(x, dict):
+            return self._fused.predict(x, batch_size)
+        self.sync()
         n = len(next(iter(x.values()))) if isinstance(x, dict) else len(x[0] if isinstance(x, (list, tuple)) else x)
         bs = batch_size or n
         outs = []
@@ -425,8 +451,18 @@ class Model:
     def compile(self, optimizer=None, loss=None, **kwargs):
         self.optimizer = optimizer if optimizer is not None else Adam()
         self.loss = loss if loss is not None else binary_crossentropy
+        self._fused = None
+        if self.fuse and self.loss is binary_crossentropy and isinstance(self.optimizer, (Adam, SGD)):
+            from .lowering import lower  # a DeepFM-shaped graph runs on the fused engine (one lookup, tcgen05 towers)
+
+            self._fused = lower(self)
 
     def train_on_batch(self, x, y) -> float:
+        if self._fused is not None and isinstance(x, dict):
+            n = len(np.asarray(next(iter(x.values()))))
+            self._fused.build(n, self.optimizer)
+            return self._fused.train_on_batch(x, y) + self._fused.reg_loss()
+        self.sync()
         out = self(x, training=True)
         yt = torch.as_tensor(np.asarray(y), dtype=torch.float32).to(device()) if not isinstance(y, torch.Tensor) else y.to(device())
         loss = self.loss(yt, out)
@@ -434,28 +470,65 @@ class Model:
         for p, _ in params:
             p.grad = None
         loss.backward()
+        sparse = [l for l in self._all_layers() if getattr(l, "_sparse_grads", None)]
+        skip = {id(l.embeddings) for l in sparse}
         # Keras adds the regularisation losses to the reported loss; their gradient 2*l2*W is applied inside the update kernels
-        reg = sum(float(l2) * float((p.detach() * p.detach()).sum()) for p, l2 in params if l2)
+        # (tables under the sparse row update are left out of the reported term: a full pass over them is what that update avoids)
+        reg = sum(float(l2) * float((p.detach() * p.detach()).sum()) for p, l2 in params if l2 and id(p) not in skip)
         self.optimizer.step(params)
+        for l in sparse:  # large tables: IndexedSlices-style gradient -> sorted-segment row update
+            l.apply_sparse(self.optimizer)
         self._update_moving_stats()
         return float(loss.detach()) + reg
 
-    def _update_moving_stats(self):
+    def save_weights(self, filepath, **kwargs):
+        """keras.Model.save_weights: a directory of `.npy` files (tables row-sharded), see handyrec_b200.checkpoint."""
+        from .checkpoint import save_weights
+
+        save_weights(self, filepath)
+
+    def load_weights(self, filepath, **kwargs):
+        from .checkpoint import load_weights
+
+        load_weights(self, filepath)
+
+    def _all_layers(self):
+        out, seen = [], set()
         for l in self.layers:
             for sub in [l] + _all_sublayers(l):
-                fn = getattr(sub, "_commit_moving_stats", None)
-                if fn:
-                    fn()
+                if id(sub) not in seen:
+                    seen.add(id(sub))
+                    out.append(sub)
+        return out
+
+    def _update_moving_stats(self):
+        for sub in self._all_layers():
+            fn = getattr(sub, "_commit_moving_stats", None)
+            if fn:
+                fn()
 
     def fit(self, x=None, y=None, batch_size=32, epochs=1, validation_data=None, verbose=0, **kwargs):
         history = {"loss": []}
+        if isinstance(x, tuple) and len(x) == 2 and isinstance(x[0], dict) and y is None:
+            x, y = x
         batches = _batches(x, y, batch_size)
         for _ in range(epochs):
-            tot, cnt = 0.0, 0
-            for xb, yb in batches():
-                tot += self.train_on_batch(xb, yb)
-                cnt += 1
-            history["loss"].append(tot / max(cnt, 1))
+            if self._fused is not None and isinstance(x, dict):
+                # dict-of-arrays input: batches are packed into pinned memory one step ahead of the GPU and the whole epoch
+                # runs on the fused engine with asynchronous loss read-back (lowering.FusedDeepFM.fit_epoch)
+                n = len(np.asarray(next(iter(x.values()))))
+                self._fused.build(min(batch_size, n), self.optimizer)
+                losses = self._fused.fit_epoch(x, y, batch_size)
+                sizes = [min(batch_size, n - s) for s in range(0, n, batch_size)]
+                history["loss"].append(float(np.average(losses, weights=sizes)) + self._fused.reg_loss())
+                self.last_losses = losses
+            else:
+                tot, cnt = 0.0, 0
+                for xb, yb in batches():
+                    tot += self.train_on_batch(xb, yb)
+                    cnt += 1
+                history["loss"].append(tot / max(cnt, 1))
+            self.sync()
             if validation_data is not None:
                 vl, vc = 0.0, 0
                 with torch.no_grad():

@@ -4,6 +4,6 @@ from .core import DNN
 from .interaction import FM
 from .sequence import SequencePoolingLayer, LocalActivationUnit
 from .activation import Dice
-from .tools import ValueTable, CustomEmbedding, SqueezeMask, AttentionPooling
+from .tools import ValueTable, ValueRows, CustomEmbedding, SqueezeMask, AttentionPooling, SampledSoftmaxLayer
 
-__all__ = ["DNN", "FM", "SequencePoolingLayer", "Dice", "ValueTable", "CustomEmbedding", "SqueezeMask", "LocalActivationUnit", "AttentionPooling"]
+__all__ = ["DNN", "FM", "SequencePoolingLayer", "Dice", "ValueTable", "CustomEmbedding", "SqueezeMask", "LocalActivationUnit", "AttentionPooling", "SampledSoftmaxLayer", "ValueRows"]

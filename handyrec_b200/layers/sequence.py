@@ -44,9 +44,38 @@ class LocalActivationUnit(Layer):
         self.dnn.build((None, input_shape[1][1], 4 * d))
         self.built = True
 
+    def _fused_inference(self, query, keys):
+        """Inference (no gradient, moving Dice statistics): hrb_lau_fwd gathers q and the T keys from the table, builds
+        [q,k,q-k,q*k] per tile in shared memory, runs the MLP, masks padded positions -- the (B,T,4D) tensor never exists."""
+        from .. import kernels as K
+        from .activation import Dice
+        from .core import Dense
+
+        src_q, src_k = getattr(query, "_hrb_src", None), getattr(keys, "_hrb_src", None)
+        dnn = self.dnn
+        if src_q is None or src_k is None or src_q[0] is not src_k[0] or dnn.use_bn or torch.is_grad_enabled():
+            return None
+        if dnn.activation not in ("dice", "relu", "sigmoid", "tanh", "linear", None) or dnn.output_activation not in (None, "linear"):
+            return None
+        dense = [l for l in dnn.layers if isinstance(l, Dense)]
+        dices = [l for l in dnn.layers if isinstance(l, Dice)]
+        if dnn.activation == "dice" and len(dices) != len(dense) - 1:
+            return None
+        stats = [(d.alphas.data, d.moving_mean.data, d.moving_variance.data) for d in dices] if dnn.activation == "dice" else None
+        params = K.lau_pack_params([d.kernel.data for d in dense], [d.bias.data for d in dense], stats)
+        table, q_ids = src_q
+        _, k_ids = src_k
+        score, _ = K.lau_fwd(table, q_ids.reshape(-1).contiguous(), k_ids.contiguous(), params, [d.units for d in dense], dnn.activation or "linear",
+                             want_pooled=False)
+        return score
+
     def call(self, inputs, mask=None, **kwargs):
         query, keys = inputs  # (?, 1, D), (?, T, D)
         key_mask = mask[1]    # (?, T) after SqueezeMask
+        if not kwargs.get("training", False):
+            fused = self._fused_inference(query, keys)
+            if fused is not None:
+                return fused
         B, T, D = keys.shape
         att_input = AttInputFn.apply(query.reshape(B, D), keys)                  # sequence.py:96-97
         att_out = self.dnn(att_input, training=kwargs.get("training", False))     # (?, T, 1)

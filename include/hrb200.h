@@ -293,10 +293,49 @@ int hrb_sigmoid_bce(const float* dnn_logit, const float* fm_logit, const float* 
 int hrb_clipped_bce(const float* prob, const float* label, int64_t n, float eps, float grad_scale, float* dprob,
                     float* loss_sum, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * (f1) retrieval loss: SampledSoftmaxLayer.call = tf.nn.sampled_softmax_loss (layers/tools.py:56-75), TF defaults:
+ *   num_true = 1, remove_accidental_hits, subtract log Q, log-uniform candidates drawn unique.
+ *   true_logit[b] = <user_b, item_label(b)> (hrb_rowdot), sampled_logit[b,j] = <user_b, item_sampled(j)> (hrb_dense_bwd_x as A.B^T);
+ *   this entry applies - log Q, masks sampled(j) == label(b) with -FLT_MAX and takes the softmax cross-entropy against class 0:
+ *   loss[b] = logsumexp(z) - z_0; with gradient buffers also d_true_logit / d_sampled_logit (times gout[b], NULL = 1).
+ *   Q(k) = -expm1(num_tries*log1p(-p_k)), p_k = log((k+2)/(k+1))/log(range_max+1) -- or the caller's own expected counts
+ *   (true_expected (B), sampled_expected (S); both or none), which is how `sampled_values` are injected for parity tests.
+ * tf.nn.l2_normalize(x) WITHOUT an axis, as DSSM calls it (models/retrieval/DSSM.py:105-106): y = x * rsqrt(max(sum x^2, eps))
+ *   over the whole tensor; stat (1 float) keeps the factor for the backward; scratch: 256 floats; fixed-order reductions.
+ * ------------------------------------------------------------------------------------------ */
+int hrb_sampled_softmax(const float* true_logit, const float* sampled_logit, int64_t ld, const int32_t* labels,
+                        const int32_t* sampled, int64_t batch, int32_t num_sampled, const float* true_expected,
+                        const float* sampled_expected, float num_tries, int64_t range_max, int32_t remove_accidental_hits,
+                        const float* gout, float* loss, float* d_true_logit, float* d_sampled_logit, void* stream);
+int hrb_rowdot(const float* a, int64_t lda, const float* b, int64_t ldb, int64_t M, int32_t K, float* out, void* stream);
+int hrb_rowscale(const float* x, int64_t ldx, const float* s, int64_t M, int32_t K, float* out, int64_t ldo, void* stream);
+int hrb_l2_normalize_fwd(const float* x, int64_t n, float eps, float* y, float* stat, float* scratch, void* stream);
+int hrb_l2_normalize_bwd(const float* y, const float* dy, int64_t n, const float* stat, float* dx, float* scratch, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * (f4) top-n inner-product search: faiss.IndexFlatIP.search(user_embd, n) of handyrec/models/utils.py:7-51.
+ *   The caller computes the scores of a chunk of items (queries . items^T, e.g. hrb_dense_bwd_x_t) and folds every chunk into the
+ *   running lists: best_val / best_idx (queries, k), ordered by (score descending, item index ascending); hrb_topk_init first.
+ * ------------------------------------------------------------------------------------------ */
+int hrb_topk_init(float* best_val, int32_t* best_idx, int64_t queries, int32_t k, void* stream);
+int hrb_topk_merge(const float* scores, int64_t ld, int64_t queries, int32_t n_cols, int64_t col_base, int32_t k, float* best_val,
+                   int32_t* best_idx, void* stream);
+
 /* a8 concat glue (layers/utils.py:28-36,70-84): dense features (fp32, or int32 cast to fp32) go to the
  * head columns of the DNN input row; columns [n, n_pad) are zero-filled (alignment padding). */
 int hrb_pack_dense(const void* src, int32_t src_is_int32, int64_t src_ld, int64_t batch, int32_t n, int32_t n_pad,
                    float* dst, int64_t dst_ld, void* stream);
+
+/* a3 input glue, HOST side (the only entry points that take host pointers and run on the CPU; no device work).
+ * FeatureGroup.construct_inputs (features/group.py:218-248) hands Keras one array per feature; the fused lookup takes one
+ * packed int32 id matrix and one fp32 dense matrix per batch (a7/a8).  Rows [row_start, row_start+rows) of every column array
+ * cols_host[c] (row-major, ld_host[c] elements per row, width_host[c] used; dtype_host[c]: 0 int32, 1 int64, 2 float32, 3
+ * float64) are converted and written side by side into dst_host[rows, dst_ld] by a persistent thread pool (n_threads <= 0: all). */
+int hrb_host_pack_i32(const void* const* cols_host, const int32_t* dtype_host, const int64_t* width_host, const int64_t* ld_host,
+                      int32_t n_cols, int64_t row_start, int64_t rows, int32_t* dst_host, int64_t dst_ld, int32_t n_threads);
+int hrb_host_pack_f32(const void* const* cols_host, const int32_t* dtype_host, const int64_t* width_host, const int64_t* ld_host,
+                      int32_t n_cols, int64_t row_start, int64_t rows, float* dst_host, int64_t dst_ld, int32_t n_threads);
 
 /* Dense-parameter optimisers on a flat fp32 buffer (Keras Adam / SGD formulas). */
 int hrb_adam_step(float* param, const float* grad, float* m, float* v, int64_t n, float lr, float beta1,

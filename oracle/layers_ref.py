@@ -55,6 +55,10 @@ __all__ = [
     "embedding_grad_dense",
     "sharded_lookup_emulated",
     "sampledsoftmaxloss",
+    "log_uniform_prob",
+    "log_uniform_sample",
+    "unique_expected_count",
+    "sampled_softmax_loss",
 ]
 
 
@@ -400,6 +404,60 @@ def l2_normalize(x: torch.Tensor, axis=None, eps: float = 1e-12) -> torch.Tensor
 def sampledsoftmaxloss(y_true, y_pred):
     """layers/utils.py:99-114: ``tf.reduce_mean(y_pred)``."""
     return as_t(np.asarray(y_pred, dtype=np.float32)).mean()
+
+
+# ----------------------------------------------------------------------------
+# (f1) tf.nn.sampled_softmax_loss as SampledSoftmaxLayer uses it (layers/tools.py:56-75)
+# ----------------------------------------------------------------------------
+def log_uniform_prob(ids, range_max: int):
+    """P(k) of TF's log-uniform (Zipfian) candidate sampler: log((k+2)/(k+1)) / log(range_max+1)."""
+    k = np.asarray(ids, dtype=np.float64)
+    return np.log((k + 2.0) / (k + 1.0)) / np.log(range_max + 1.0)
+
+
+def log_uniform_sample(num_sampled: int, range_max: int, rng: np.random.RandomState):
+    """``tf.random.log_uniform_candidate_sampler(unique=True)`` restated: draw ``floor(exp(u*log(range_max+1))) - 1 mod range_max``
+    until ``num_sampled`` distinct classes are in hand.  Returns (sampled ids in draw order, number of tries).
+    The random stream is numpy's, not TF's: only the DISTRIBUTION matches (statistical parity); numeric parity tests inject the
+    sampled values on both sides."""
+    seen, out, tries = set(), [], 0
+    log_range = np.log(range_max + 1.0)
+    while len(out) < num_sampled:
+        tries += 1
+        k = int(np.exp(rng.random_sample() * log_range)) - 1
+        k %= range_max
+        if k not in seen:
+            seen.add(k)
+            out.append(k)
+    return np.asarray(out, dtype=np.int32), tries
+
+
+def unique_expected_count(p, num_tries: int):
+    """Expected count of a class under the unique sampler: 1 - (1-p)^num_tries = -expm1(num_tries * log1p(-p))."""
+    return -np.expm1(num_tries * np.log1p(-np.asarray(p, dtype=np.float64)))
+
+
+def sampled_softmax_loss(weights: torch.Tensor, biases: torch.Tensor, labels: torch.Tensor, inputs: torch.Tensor, sampled: torch.Tensor,
+                         true_expected: torch.Tensor, sampled_expected: torch.Tensor, remove_accidental_hits: bool = True) -> torch.Tensor:
+    """nn_impl._compute_sampled_logits + softmax cross-entropy (TF 2.x defaults: num_true = 1, subtract_log_q = True).
+
+    weights (C, D), biases (C,), labels (B,) or (B,1) int, inputs (B, D), sampled (S,) int; expected counts as the candidate
+    sampler returns them.  -> loss (B,).  Op order follows TF: gather both weight sets, true logits as a row-wise product sum,
+    sampled logits as a matmul with the transposed sampled weights, accidental hits get -FLOAT_MAX added, log Q subtracted,
+    labels one-hot on column 0, softmax_cross_entropy_with_logits."""
+    labels = as_t(labels).long().reshape(-1)
+    sampled = as_t(sampled).long().reshape(-1)
+    true_w = weights[labels]                       # embedding_lookup(weights, labels)
+    sampled_w = weights[sampled]
+    true_logits = (inputs * true_w).sum(1) + biases[labels]
+    sampled_logits = inputs @ sampled_w.t() + biases[sampled]
+    if remove_accidental_hits:
+        hit = labels[:, None] == sampled[None, :]
+        sampled_logits = sampled_logits + hit.to(sampled_logits.dtype) * (-torch.finfo(torch.float32).max)
+    true_logits = true_logits - torch.log(as_t(true_expected, torch.float32).reshape(-1))
+    sampled_logits = sampled_logits - torch.log(as_t(sampled_expected, torch.float32).reshape(1, -1))
+    logits = torch.cat([true_logits[:, None], sampled_logits], 1)
+    return torch.logsumexp(logits, 1) - logits[:, 0]
 
 
 # ----------------------------------------------------------------------------

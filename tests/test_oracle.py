@@ -78,3 +78,29 @@ def test_concat_layout_and_errors():
     assert oracle.concat([], e, axis=1, keepdims=True).shape == (2, 3, 4)
     assert oracle.concat([d[0]], []).shape == (2, 1)
     assert oracle.concat([], e).shape == (2, 12)
+
+
+def test_log_uniform_sampler_distribution_and_uniqueness():
+    """Host sampler of SampledSoftmaxLayer vs the closed-form log-uniform probabilities; draws are unique; the oracle's restatement
+    and the layer's vectorised sampler follow the same law."""
+    import numpy as np
+
+    from handyrec_b200.layers.tools import LogUniformSampler
+
+    C = 50
+    s = LogUniformSampler(C, seed=1)
+    counts = np.zeros(C)
+    n = 20000
+    for _ in range(n):
+        ids, tries = s.sample(1)
+        assert tries >= 1
+        counts[ids[0]] += 1
+    p = oracle.log_uniform_prob(np.arange(C), C)
+    assert abs(p.sum() - 1.0) < 1e-12
+    assert np.abs(counts / n - p).max() < 4 * np.sqrt(p.max() / n)
+    ids, tries = s.sample(20)
+    assert len(set(ids.tolist())) == 20 and tries >= 20 and ids.dtype == np.int32
+    ids, _ = LogUniformSampler(7, seed=0).sample(100)  # more candidates than classes: every class once
+    assert sorted(ids.tolist()) == list(range(7))
+    e = oracle.unique_expected_count(p, 30)
+    assert np.all((e > 0) & (e <= 1)) and np.all(np.diff(e) < 0)

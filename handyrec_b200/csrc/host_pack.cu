@@ -10,6 +10,7 @@
 #include <functional>
 #include <mutex>
 #include <thread>
+#include <type_traits>
 #include <vector>
 
 #include "common.cuh"
@@ -76,15 +77,6 @@ Pool& pool() {
 }
 std::mutex g_pack_mu;  // one packing job at a time (the pool is shared)
 
-template <typename D, typename S>
-inline void copy_block(const S* src, int64_t src_ld, int64_t width, int64_t r0, int64_t r1, D* dst, int64_t dst_ld) {
-  for (int64_t r = r0; r < r1; ++r) {
-    const S* s = src + r * src_ld;
-    D* d = dst + (r - r0) * dst_ld;
-    for (int64_t c = 0; c < width; ++c) d[c] = (D)s[c];
-  }
-}
-
 template <typename D>
 int pack(const void* const* cols, const int32_t* dtype, const int64_t* width, const int64_t* ld, int32_t n_cols, int64_t row_start,
          int64_t rows, D* dst, int64_t dst_ld, int32_t n_threads) {
@@ -94,19 +86,41 @@ int pack(const void* const* cols, const int32_t* dtype, const int64_t* width, co
   int nt = n_threads <= 0 ? p.size() : std::min(n_threads, p.size());
   if (rows < 4096) nt = 1;
   const int64_t per = (rows + nt - 1) / nt;
+  // row-major walk: a destination row (a few hundred bytes) is written in one go while every source column is read as its own
+  // sequential stream -- the per-column walk this replaces spent ~6 ns per element on strided stores
+  bool simple = true;  // every column is one element wide and already has the destination's element size (int32->int32, f32->f32)
+  for (int c = 0; c < n_cols; ++c) simple = simple && width[c] == 1 && dtype[c] == (std::is_same<D, int32_t>::value ? 0 : 2);
   auto work = [&](int t) {
     const int64_t a = row_start + t * per, b = std::min(row_start + rows, a + per);
     if (a >= b) return;
-    int64_t col0 = 0;
-    for (int c = 0; c < n_cols; ++c) {
-      D* d = dst + (a - row_start) * dst_ld + col0;
-      switch (dtype[c]) {
-        case 0: copy_block(static_cast<const int32_t*>(cols[c]), ld[c], width[c], a, b, d, dst_ld); break;
-        case 1: copy_block(static_cast<const int64_t*>(cols[c]), ld[c], width[c], a, b, d, dst_ld); break;
-        case 2: copy_block(static_cast<const float*>(cols[c]), ld[c], width[c], a, b, d, dst_ld); break;
-        default: copy_block(static_cast<const double*>(cols[c]), ld[c], width[c], a, b, d, dst_ld); break;
+    if (simple) {
+      // blocks of 256 rows: every source column is read as one sequential 1 KB run (prefetcher-friendly; 39 interleaved streams
+      // are not), the 256 x n_cols destination block stays in L1/L2 while its columns are filled
+      constexpr int64_t RB = 256;
+      for (int64_t r0 = a; r0 < b; r0 += RB) {
+        const int64_t r1 = std::min(b, r0 + RB);
+        D* d0 = dst + (r0 - row_start) * dst_ld;
+        for (int c = 0; c < n_cols; ++c) {
+          const D* s = static_cast<const D*>(cols[c]);
+          const int64_t l = ld[c];
+          D* d = d0 + c;
+          for (int64_t r = r0; r < r1; ++r, d += dst_ld) *d = s[r * l];
+        }
       }
-      col0 += width[c];
+      return;
+    }
+    for (int64_t r = a; r < b; ++r) {
+      D* d = dst + (r - row_start) * dst_ld;
+      for (int c = 0; c < n_cols; ++c) {
+        const int64_t w = width[c];
+        switch (dtype[c]) {
+          case 0: { const int32_t* s = static_cast<const int32_t*>(cols[c]) + r * ld[c]; for (int64_t k = 0; k < w; ++k) d[k] = (D)s[k]; break; }
+          case 1: { const int64_t* s = static_cast<const int64_t*>(cols[c]) + r * ld[c]; for (int64_t k = 0; k < w; ++k) d[k] = (D)s[k]; break; }
+          case 2: { const float* s = static_cast<const float*>(cols[c]) + r * ld[c]; for (int64_t k = 0; k < w; ++k) d[k] = (D)s[k]; break; }
+          default: { const double* s = static_cast<const double*>(cols[c]) + r * ld[c]; for (int64_t k = 0; k < w; ++k) d[k] = (D)s[k]; break; }
+        }
+        d += w;
+      }
     }
   };
   if (nt == 1) work(0); else p.run(nt, work);

@@ -524,9 +524,10 @@ class Model:
                 self.last_losses = losses
             else:
                 tot, cnt = 0.0, 0
-                for xb, yb in batches():
-                    tot += self.train_on_batch(xb, yb)
-                    cnt += 1
+                for xb, yb in batches():  # Keras reports the sample-weighted running mean of the batch losses
+                    nb = len(yb) if hasattr(yb, "__len__") else 1
+                    tot += self.train_on_batch(xb, yb) * nb
+                    cnt += nb
                 history["loss"].append(tot / max(cnt, 1))
             self.sync()
             if validation_data is not None:

@@ -53,7 +53,7 @@ class LocalActivationUnit(Layer):
 
         src_q, src_k = getattr(query, "_hrb_src", None), getattr(keys, "_hrb_src", None)
         dnn = self.dnn
-        if src_q is None or src_k is None or src_q[0] is not src_k[0] or dnn.use_bn or torch.is_grad_enabled():
+        if src_q is None or src_k is None or src_q[0].data_ptr() != src_k[0].data_ptr() or dnn.use_bn or torch.is_grad_enabled():
             return None
         if dnn.activation not in ("dice", "relu", "sigmoid", "tanh", "linear", None) or dnn.output_activation not in (None, "linear"):
             return None

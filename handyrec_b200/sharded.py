@@ -215,6 +215,11 @@ class RowExchange:
             self._grad_wait()
         if mark is not None:
             mark("grad_rows_all_to_all")
+        if self._grad_recv.is_cuda:  # this may run on another stream than the one the buffers were allocated on
+            cur = torch.cuda.current_stream()
+            self._grad_recv.record_stream(cur)
+            self._grad_send.record_stream(cur)
+            self.recv_keys.record_stream(cur)
         self.p.keyed_update(self.recv_keys, self._grad_recv, self.n_recv, op)
         self._grad_send = self._grad_recv = self._grad_wait = None
         if mark is not None:
@@ -320,22 +325,41 @@ class ShardedDeepFMEngine(DeepFMEngine):
             if self._timeline is not None:
                 self._mark("route_keys_all_to_all")
 
+    _side2 = None
+
     def _embedding_backward(self, ids, B, st, op):
+        cur = torch.cuda.current_stream()
+        own_stream = False
         if self.exchange is not None:  # gradient rows of the sharded tables go on the wire first: the transfer runs beside the local reduction
             self.exchange.backward_start(ids, self.dX0)
-        if self.plan_rep is not None:  # replicated tables: local sorted-segment reduction into the flat gradient buffer
+            # the owner-side row update of the sharded tables only needs the all-to-all: it gets a stream of its own so that it
+            # starts the moment the rows land instead of queueing behind the replicated tables' reduction (round 1: 0.23 ms of tail)
+            own_stream = self._marks is None and self.plan_rep is not None and self.dX0.is_cuda
+            if own_stream:
+                if self._side2 is None:
+                    self._side2 = torch.cuda.Stream()
+                self._side2.wait_stream(cur)
+                with torch.cuda.stream(self._side2):
+                    self._finish_sharded(op)
+        if self.plan_rep is not None:  # replicated tables: local reduction into the flat gradient buffer
             self._zero_table_grads()
             call("hrb_lookup_bwd_update", self.plan_rep._h, K._p(ids), ids.stride(0), B, K._p(self.dX0), self.K0p, None, ctypes.byref(op),
-                 K._p(self._ws_rep), self._ws_rep.numel(), st)
+                 K._p(self._ws_rep), self._ws_rep.numel(), K._stream())
             self._rep_done = torch.cuda.Event()
             self._rep_done.record()
             self._mark("replicated_embedding_bwd")
         if self.exchange is not None:
-            self.exchange.backward_finish(op, mark=self._mark if self._timeline is not None else None)
-            if self.peer_lookup:
-                # peers read this shard in the next forward: nobody may start it before every rank has finished updating
-                self.comm.all_reduce_sum(self._barrier_buf)
+            if own_stream:
+                cur.wait_stream(self._side2)
+            else:
+                self._finish_sharded(op)
             self._mark("sharded_embedding_bwd_update")
+
+    def _finish_sharded(self, op):
+        self.exchange.backward_finish(op, mark=self._mark if self._timeline is not None else None)
+        if self.peer_lookup:
+            # peers read this shard in the next forward: nobody may start it before every rank has finished updating
+            self.comm.all_reduce_sum(self._barrier_buf)
 
     def _sync_dense_grads(self):
         if self._rep_done is not None:  # recorded on the side stream when the embedding backward is overlapped

@@ -5,6 +5,8 @@
       STEPS        = number of training steps the profiled command ran (warm-up + timed + e2e + per-phase profile step)
   python profiles/summarize.py full gpurun_out/full_raw.csv > profiles/rNN_ncu_full.md
       full_raw.csv = `ncu -i capture.ncu-rep --page raw --csv`
+  python profiles/summarize.py json gpurun_out/full_raw.csv profiles/rNN_ncu_full.json
+      per-launch dram bytes / duration / tensor-pipe numbers as JSON: bench.py reads `roofline.traffic` from this file
 """
 import csv
 import io
@@ -83,7 +85,43 @@ def full(path):
         print(f"| `{short(r.get('Kernel Name', '?'))}` | " + " | ".join(cells) + " |")
 
 
+def _num(cell, unit):
+    v = float(str(cell).replace(",", ""))
+    u = (unit or "").lower()
+    scale = {"byte": 1.0, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9, "ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6,
+             "nsecond": 1e-3, "usecond": 1.0, "msecond": 1e3, "second": 1e6}
+    return v * scale.get(u, 1.0)
+
+
+def to_json(path, out):
+    import json
+
+    rows = read_ncu_csv(path)
+    units, cols = rows[0], list(rows[0].keys())
+
+    def col(m):
+        return next((c for c in cols if c == m or c.startswith(m)), None)
+
+    ker = []
+    for r in rows[1:]:
+        try:
+            ker.append({"name": short(r.get("Kernel Name", "?")),
+                        "duration_us": _num(r[col("gpu__time_duration.sum")], units[col("gpu__time_duration.sum")]),
+                        "dram_read_bytes": _num(r[col("dram__bytes_read.sum")], units[col("dram__bytes_read.sum")]),
+                        "dram_write_bytes": _num(r[col("dram__bytes_write.sum")], units[col("dram__bytes_write.sum")]),
+                        "tensor_pipe_active_pct": float(r[col("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active")] or 0),
+                        "warps_active_pct": float(r[col("sm__warps_active.avg.pct_of_peak_sustained_active")] or 0),
+                        "regs_per_thread": float(r[col("launch__registers_per_thread")] or 0)})
+        except (KeyError, TypeError, ValueError):
+            continue
+    json.dump({"source": path, "kernels": ker}, open(out, "w"), indent=1)
+    print(f"{out}: {len(ker)} launches")
+
+
 if __name__ == "__main__":
+    if len(sys.argv) >= 4 and sys.argv[1] == "json":
+        to_json(sys.argv[2], sys.argv[3])
+        raise SystemExit(0)
     if len(sys.argv) >= 4 and sys.argv[1] == "launches":
         launches(sys.argv[2], float(sys.argv[3]))
     elif len(sys.argv) >= 3 and sys.argv[1] == "full":

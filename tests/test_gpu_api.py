@@ -238,8 +238,18 @@ def test_retrieval_models_fit_like_the_reference_tests(dev):
         M.YouTubeMatchDNN(ug2, ug2)
     m2 = M.YouTubeMatchDNN(ug2, ig2, dnn_hidden_units=(16, 8), num_sampled=10)
     m2.compile(optimizer=KL.Adam(2e-2), loss=sampledsoftmaxloss)
-    h2 = m2.fit(x=batches, epochs=6)
-    assert h2.history["loss"][-1] < h2.history["loss"][0]
+    h2 = m2.fit(x=batches, epochs=2)  # fresh candidates every step (the layer's own log-uniform sampler)
+    assert np.isfinite(h2.history["loss"]).all()
+    # with the candidates pinned the objective is fixed, and training on one batch must bring it down
+    from handyrec_b200.layers import SampledSoftmaxLayer
+
+    ssl = [l for l in m2.layers if isinstance(l, SampledSoftmaxLayer)][0]
+    sampled, tries = oracle.log_uniform_sample(10, n_items, np.random.RandomState(5))
+    lab = batches[0][0]["movie_id"].reshape(-1)
+    ssl.sampled_values = (sampled, oracle.unique_expected_count(oracle.log_uniform_prob(lab, n_items), tries),
+                          oracle.unique_expected_count(oracle.log_uniform_prob(sampled, n_items), tries))
+    losses = [m2.train_on_batch(*batches[0]) for _ in range(15)]
+    assert losses[-1] < 0.8 * losses[0]
 
 
 def test_large_table_takes_sparse_row_updates(dev):

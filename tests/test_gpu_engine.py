@@ -217,8 +217,7 @@ def test_engine_step_at_bench_configuration(dev, optimizer):
         if optimizer == "sgd":
             close(((tables[t] - got) / lr)[clean], gr[clean], 1e-4)  # the row gradients themselves (dense-updated and in-place tables alike)
         else:
+            # |g| ~ 1e-7 here (1/B-scaled), i.e. next to eps = 1e-7: the step is ~linear in g and well conditioned
             want = tables[t] - lr_t * (0.1 * gr) / ((0.001 * gr * gr).sqrt() + 1e-7)
-            ok = ((gr.abs() > 1e-9).all(1) | ~touched) & clean  # m/(sqrt(v)+eps) is ill-conditioned where the summed gradient is ~0
-            assert float(ok.float().mean()) > 0.5
-            close(got[ok], want[ok], 2e-4)
+            close(got[clean], want[clean], 2e-4)
         assert torch.equal(got[~touched], tables[t][~touched])

@@ -214,6 +214,9 @@ def main():
                     help="tables up to this many rows take the dense (Keras-exact) optimiser step; at N>1 they are replicated instead of sharded (0 = off)")
     ap.add_argument("--large-table-rows", type=int, default=0, help="C4: give every table above --small-table-rows this many rows (e.g. 100000000 at --gpus 8)")
     ap.add_argument("--scale-vocab", type=float, default=1.0, help="shrink every vocabulary (debug only; reported in config)")
+    ap.add_argument("--bwd-algo", default="auto", choices=["auto", "units", "sort"],
+                    help="embedding backward: auto = the engine times both implementations in its first steps and keeps the faster one; "
+                         "units / sort pin one (profiling under ncu distorts the trial timings)")
     ap.add_argument("--verify", action="store_true", help="N>1: 3 sharded steps at a small batch compared with a single-GPU engine on the concatenated batch")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -273,6 +276,14 @@ def main():
         eng = ShardedDeepFMEngine(tables, vocabs, fields, N_DENSE, comm, peer_ptrs=None if args.no_peer_lookup else peer_ptrs,
                                   dnn_hidden_units=DNN_HIDDEN, dnn_activation="relu", batch_size=B, optimizer=args.optimizer, lr=1e-3,
                                   l2_embd=0.0, seed=2022, replicate_max_rows=args.small_table_rows)
+    if args.bwd_algo != "auto":
+        from handyrec_b200 import _lib
+        from handyrec_b200._lib import call
+
+        eng.autotune_embedding_bwd = False
+        eng.bwd_algo = args.bwd_algo
+        for pl in [eng.plan] + [p for p in (getattr(eng, "plan_rep", None),) if p is not None]:
+            call("hrb_plan_set_bwd_algo", pl._h, _lib.BWD_UNITS if args.bwd_algo == "units" else _lib.BWD_SORT)
     NB = 4  # rotating pool of distinct batches (tables are 6.5 GB >> 126 MB L2: every step touches fresh rows)
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
     ids_pool, dense_pool, label_pool = [], [], []

@@ -48,6 +48,7 @@ constexpr int UB_STACK = 256;
 constexpr int UB_WARPS = UB_THREADS / 32;
 constexpr int UB_HELPERS = 4;                // CTAs per unit; all but the first only work when the unit overflows
 constexpr int UB_TILE = 4096;                // samples per split tile
+constexpr int SPLIT_ROUNDS = UB_TILE / UB_WARPS / 32;  // rounds of 32 samples a warp of the split kernel walks
 constexpr uint32_t UB_INVALID = 0xFFFFFFFFu;
 constexpr uint32_t UB_NONE = 0xFFFFFFFEu;
 constexpr int UB_SLICE_TARGET = 4096;        // positions per slice of a row the host knows to be hot
@@ -131,7 +132,7 @@ struct SplitArgs {
   uint32_t* ent_pos;    // (local column << 24) | sample
 };
 
-// warp w of the CTA walks samples [chunk*4096 + w*512, +512) of the tile's column in 16 rounds of 32 (coalesced)
+// warp w of the CTA walks samples [chunk*4096 + w*512, +512) of the tile's column in SPLIT_ROUNDS rounds of 32 (coalesced)
 template <bool SCATTER>
 __global__ void __launch_bounds__(UB_THREADS) split_kernel(SplitArgs a) {
   __shared__ uint32_t wcnt[UB_WARPS][UB_MAX_BINS];
@@ -142,9 +143,9 @@ __global__ void __launch_bounds__(UB_THREADS) split_kernel(SplitArgs a) {
   __syncthreads();
   const uint32_t* colp = a.idsT + (int64_t)tile.pos_col * a.ldT;
   const int64_t b0 = (int64_t)tile.chunk * UB_TILE + w * (UB_TILE / UB_WARPS);
-  uint32_t packed[UB_IPT];  // SCATTER: (bin << 16) | rank inside (warp, bin)
+  uint32_t packed[SPLIT_ROUNDS];  // SCATTER: (bin << 16) | rank inside (warp, bin)
 #pragma unroll
-  for (int k = 0; k < UB_IPT; ++k) {
+  for (int k = 0; k < SPLIT_ROUNDS; ++k) {
     const int64_t b = b0 + k * 32 + lane;
     const uint32_t id = b < a.ldT ? __ldg(colp + b) : UB_INVALID;
     const uint32_t bin = id == UB_INVALID ? UB_INVALID : id >> ts.shift;
@@ -184,7 +185,7 @@ __global__ void __launch_bounds__(UB_THREADS) split_kernel(SplitArgs a) {
   __syncthreads();
   const uint32_t mask = (1u << ts.shift) - 1u;
 #pragma unroll
-  for (int k = 0; k < UB_IPT; ++k) {
+  for (int k = 0; k < SPLIT_ROUNDS; ++k) {
     if (packed[k] == UB_INVALID) continue;
     const int64_t b = b0 + k * 32 + lane;
     const uint32_t id = __ldg(colp + b);
@@ -746,7 +747,7 @@ struct UnitHost {
   int64_t expect;
 };
 
-static inline int64_t unit_ldT(int64_t batch) { return (batch + UB_IPT - 1) / UB_IPT * UB_IPT; }
+static inline int64_t unit_ldT(int64_t batch) { return (batch + 15) / 16 * 16; }  // 64-byte aligned id columns
 
 // (Re)build the unit decomposition of `plan` for `batch` samples.  Units are ordered by G, then largest first.
 static int build_units(const hrb_plan* plan, int64_t batch) {

@@ -401,3 +401,46 @@ class L2NormalizeFn(torch.autograd.Function):
         scratch = torch.empty(256, device=dy.device, dtype=torch.float32)
         call("hrb_l2_normalize_bwd", K._p(y), K._p(dy), dy.numel(), K._p(stat), K._p(dx), K._p(scratch), K._stream())
         return dx, None
+
+
+class LAUFirstLayerFn(torch.autograd.Function):
+    """First Dense of the local-activation MLP applied to [q, k, q-k, q*k] WITHOUT building that (B,T,4D) tensor
+    (layers/sequence.py:96-99 + the Dense(4D) core.py:57 prepends):  q.(Wa+Wc) + b  per sample, plus  [k | q*k].[Wb-Wc; Wd]  as one
+    B*T-row tcgen05 GEMM over 2D columns, the per-sample term added in its epilogue (hrb200.h, a10 training path)."""
+
+    @staticmethod
+    def forward(ctx, q, keys, W, b, act):
+        q, keys, W = q.contiguous(), keys.contiguous(), W.contiguous()
+        B, T, D = keys.shape
+        U = W.shape[1]
+        dev = q.device
+        wq = torch.empty(D, U, device=dev)
+        wp = torch.empty(2 * D, U, device=dev)
+        wpt = torch.empty(U, 2 * D, device=dev)
+        call("hrb_lau_split_weights", K._p(W), U, D, U, K._p(wq), K._p(wp), K._p(wpt), K._stream())
+        qterm = K.dense_fwd(q, wq, b, None, mode=_lib.GEMM_FP32)                       # (B, U): the part that does not depend on t
+        A = torch.empty(B * T, 2 * D, device=dev)
+        call("hrb_lau_pack_fwd", K._p(q), K._p(keys), B, T, D, K._p(A), K._stream())
+        y = torch.empty(B * T, U, device=dev)
+        call("hrb_dense_fwd_t_grouped", K._p(A), 2 * D, K._p(wpt), 2 * D, K._p(qterm), U, T, B * T, 2 * D, U, ACT[act], K._p(y), U, K._stream())
+        ctx.save_for_backward(q, keys, A, wq, wp, y)
+        ctx.act, ctx.has_bias, ctx.shape = act, b is not None, (B, T, D, U)
+        return y.reshape(B, T, U)
+
+    @staticmethod
+    def backward(ctx, dy):
+        q, keys, A, wq, wp, y = ctx.saved_tensors
+        B, T, D, U = ctx.shape
+        dy2 = dy.contiguous().reshape(B * T, U)
+        dz = K.act_bwd(y, dy2, ctx.act) if ctx.act not in (None, "linear") else dy2
+        dA = K.dense_bwd_x_t(dz, wp)                                                    # (B*T, 2D)
+        dwp, _ = K.dense_bwd_w_xn(A, K.transpose(dz), want_bias=False)                  # (2D, U)
+        dqterm = torch.empty(B, U, device=dz.device)
+        call("hrb_group_sum", K._p(dz), U, B, T, U, K._p(dqterm), K._stream())
+        dq = K.dense_bwd_x(dqterm, wq, mode=_lib.GEMM_FP32)                            # (B, D): through the per-sample term
+        dwq, db = K.dense_bwd_w(q, dqterm, want_bias=ctx.has_bias, mode=_lib.GEMM_FP32)
+        dk = torch.empty_like(keys)
+        call("hrb_lau_pack_bwd", K._p(q), K._p(keys), K._p(dA), B, T, D, 1, K._p(dq), K._p(dk), K._stream())
+        dW = torch.empty(4 * D, U, device=dz.device)
+        call("hrb_lau_merge_wgrads", K._p(dwq), K._p(dwp), D, U, K._p(dW), U, K._stream())
+        return dq, dk, dW, (db if ctx.has_bias else None), None

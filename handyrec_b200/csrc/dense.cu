@@ -433,6 +433,8 @@ __global__ void __launch_bounds__(256) hrb_transpose_kernel(const float* __restr
 // implemented in gemm_tc.cu (tcgen05 3xTF32); return HRB_UNSUPPORTED when the shape is not covered
 int hrb_tc_gemm_bias_act(const float* a, int64_t lda, const float* bt, int64_t ldb, const float* bias, int64_t M, int32_t N, int32_t K,
                          int32_t act, float* c, int64_t ldc, float* ct, int64_t ldct, uint32_t* relu_mask, int64_t mask_ld, cudaStream_t st);
+int hrb_tc_gemm_groupbias_act(const float* a, int64_t lda, const float* bt, int64_t ldb, const float* gbias, int64_t ldgb, int32_t group,
+                              int64_t M, int32_t N, int32_t K, int32_t act, float* c, int64_t ldc, cudaStream_t st);
 int hrb_tc_gemm_act_grad(const float* a, int64_t lda, const float* bt, int64_t ldb, int64_t M, int32_t N, int32_t K, const float* aprev,
                          int64_t ldap, int32_t act, float* c, int64_t ldc, float* ct, int64_t ldct, const uint32_t* relu_mask, int64_t mask_ld,
                          cudaStream_t st);
@@ -577,6 +579,16 @@ HRB_API int hrb_dense_bwd_x_t(const float* dz, int64_t lddz, const float* w, int
   if (M == 0) return HRB_OK;
   return hrb_tc_gemm_act_grad(dz, lddz, w, ldw, M, K, N, a_prev, lda_prev, act_prev, dx, lddx, dxt, lddxt, relu_mask, (K + 31) / 32,
                               (cudaStream_t)stream);
+}
+
+// y[M,N] = act(x[M,K] . wt[N,K]^T + group_bias[m / group_rows, :]): a Dense whose bias differs per group of consecutive rows
+HRB_API int hrb_dense_fwd_t_grouped(const float* x, int64_t ldx, const float* wt, int64_t ldwt, const float* group_bias, int64_t ldgb,
+                                    int32_t group_rows, int64_t M, int32_t K, int32_t N, int32_t act, float* y, int64_t ldy, void* stream) {
+  HRB_REQUIRE(x && wt && y && group_bias && M >= 0 && K > 0 && N > 0 && ldx >= K && ldwt >= K && ldy >= N && ldgb >= N && group_rows > 0,
+              "hrb_dense_fwd_t_grouped: bad argument");
+  HRB_REQUIRE(act >= HRB_ACT_LINEAR && act <= HRB_ACT_TANH, "hrb_dense_fwd_t_grouped: unknown activation %d", act);
+  if (M == 0) return HRB_OK;
+  return hrb_tc_gemm_groupbias_act(x, ldx, wt, ldwt, group_bias, ldgb, group_rows, M, N, K, act, y, ldy, (cudaStream_t)stream);
 }
 
 HRB_API int hrb_dense_bwd_w_t_workspace(int64_t M, int32_t K, int32_t N, size_t* bytes) {

@@ -190,6 +190,10 @@ struct Args {
   float* bsum;         // EPI_PLAIN: bsum[z*N + n] = sum over this split's k of Bt[n][k] (the bias gradient when Bt = dz^T), or NULL
   long long* trace;    // HRB_TC_TRACE: clock64 stamps of the first 64 k-blocks of CTAs 0/1 (perf debugging)
   int32_t debug;       // HRB_TC_DEBUG bit mask (perf experiments only): 1 no stores, 2 no conversion, 4 no MMA, 8 no TMA, 16 also write hi back
+  // EPI_BIAS_ACT with a bias per GROUP of rows (row m takes bias[(m / bias_group) * bias_ld + n]): the per-sample query term of the
+  // local-activation MLP's first layer (hrb_dense_fwd_t_grouped)
+  int32_t bias_group;
+  int64_t bias_ld;
 };
 
 // ATM: the A tile's hi/lo halves live in TENSOR MEMORY (written by the converter warps with tcgen05.st) instead of shared
@@ -534,7 +538,13 @@ __global__ void __launch_bounds__(THREADS, 1) gemm_tc_kernel(const __grid_consta
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
         if (EPI == EPI_BIAS_ACT) {
-          if (g.bias != nullptr) {
+          if (g.bias != nullptr && g.bias_group > 0) {
+            if (row_ok) {
+              const float* gb = g.bias + (m / g.bias_group) * g.bias_ld + n0;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] += (n0 + j < g.N) ? __ldg(gb + j) : 0.f;
+            }
+          } else if (g.bias != nullptr) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] += (n0 + j < g.N) ? __ldg(g.bias + n0 + j) : 0.f;
           }
@@ -826,6 +836,15 @@ int hrb_tc_gemm_act_grad(const float* a, int64_t lda, const float* bt, int64_t l
     return fail(HRB_UNSUPPORTED, "tcgen05 GEMM: shape/alignment not covered");
   tc::Args g{c, ct, nullptr, aprev, ldc, ldct, ldap, M, N, K, act, 1, (K + tc::BK - 1) / tc::BK, nullptr, relu_mask, mask_ld, nullptr, nullptr, 0};
   return tc::launch<128, tc::EPI_ACT_GRAD>(a, lda, bt, ldb, g, st);
+}
+// C[M,N] = act(A[M,K] * Bt[N,K]^T + gbias[m / group, :])
+int hrb_tc_gemm_groupbias_act(const float* a, int64_t lda, const float* bt, int64_t ldb, const float* gbias, int64_t ldgb, int32_t group,
+                              int64_t M, int32_t N, int32_t K, int32_t act, float* c, int64_t ldc, cudaStream_t st) {
+  if (!tc::tc_ok(a, lda, bt, ldb, M, N, K) || !aligned16(c) || ldc % 4 != 0) return fail(HRB_UNSUPPORTED, "tcgen05 GEMM: shape/alignment not covered");
+  tc::Args g{c, nullptr, gbias, nullptr, ldc, 0, 0, M, N, K, act, 1, (K + tc::BK - 1) / tc::BK, nullptr, nullptr, 0, nullptr, nullptr, 0};
+  g.bias_group = group;
+  g.bias_ld = ldgb;
+  return tc::launch<128, tc::EPI_BIAS_ACT>(a, lda, bt, ldb, g, st);
 }
 // split-K partials: part[z][M][ldp] = A[M, Kz] * Bt[N, Kz]^T ; the caller reduces over z in fixed order
 int hrb_tc_splits(int64_t M, int32_t N, int32_t K) {

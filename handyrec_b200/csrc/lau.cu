@@ -215,3 +215,144 @@ HRB_API int hrb_lau_fwd(const float* table, int64_t vocab, int32_t dim, const in
   }
   return HRB_OK;
 }
+
+// =============================================================================================
+// a10, TRAINING: the first layer of the local-activation MLP without the (B,T,4D) tensor.
+//   att_in = [q, k, q-k, q*k] (sequence.py:96-97) and W = [Wa; Wb; Wc; Wd] (4 blocks of D rows) give
+//     att_in . W = q.(Wa + Wc) + k.(Wb - Wc) + (q*k).Wd
+//   i.e. a per-SAMPLE term  qterm[b] = q[b].(Wa + Wc) + bias  (B x U, tiny)  plus a B*T-row GEMM over  A' = [k | q*k]  (2D columns
+//   instead of 4D: half the flops, half the bytes), added in the GEMM epilogue as a bias per group of T rows
+//   (hrb_dense_fwd_t_grouped).  The kernels here are the element-wise glue around the three GEMMs: weight split / gradient merge,
+//   A' and its backward, the per-sample sum of dz.  All reductions run in fixed order.
+// =============================================================================================
+namespace hrb {
+
+__global__ void __launch_bounds__(256) lau_split_weights_kernel(const float* __restrict__ W, int64_t ldw, int32_t D, int32_t U,
+                                                               float* __restrict__ wq, float* __restrict__ wp, float* __restrict__ wpt) {
+  const int total = D * U;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int d = i / U, u = i - d * U;
+    const float a = W[(int64_t)d * ldw + u], b = W[(int64_t)(D + d) * ldw + u], c = W[(int64_t)(2 * D + d) * ldw + u],
+                e = W[(int64_t)(3 * D + d) * ldw + u];
+    wq[i] = a + c;
+    wp[i] = b - c;
+    wp[(int64_t)(D + d) * U + u] = e;
+    wpt[(int64_t)u * 2 * D + d] = b - c;
+    wpt[(int64_t)u * 2 * D + D + d] = e;
+  }
+}
+
+__global__ void __launch_bounds__(256) lau_merge_wgrads_kernel(const float* __restrict__ dwq, const float* __restrict__ dwp, int32_t D, int32_t U,
+                                                              float* __restrict__ dW, int64_t ldw) {
+  const int total = D * U;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int d = i / U, u = i - d * U;
+    const float gq = dwq[i], gk = dwp[i], gm = dwp[(int64_t)(D + d) * U + u];
+    dW[(int64_t)d * ldw + u] = gq;             // Wa: through the q term
+    dW[(int64_t)(D + d) * ldw + u] = gk;       // Wb: through the k term
+    dW[(int64_t)(2 * D + d) * ldw + u] = gq - gk;  // Wc multiplies (q - k)
+    dW[(int64_t)(3 * D + d) * ldw + u] = gm;   // Wd: through q*k
+  }
+}
+
+// A'[m, :D] = k[m, :],  A'[m, D:] = q[m / T, :] * k[m, :]   (float4 granularity, D % 4 == 0)
+__global__ void __launch_bounds__(256) lau_pack_fwd_kernel(const float* __restrict__ q, const float* __restrict__ k, int64_t rows, int32_t T,
+                                                          int32_t D4, float* __restrict__ out) {
+  const int64_t total = rows * D4;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t m = i / D4;
+    const int c = (int)(i - m * D4);
+    const float4 kv = __ldg(reinterpret_cast<const float4*>(k) + i);
+    const float4 qv = __ldg(reinterpret_cast<const float4*>(q) + (m / T) * D4 + c);
+    float4* o = reinterpret_cast<float4*>(out) + m * 2 * D4;
+    o[c] = kv;
+    o[D4 + c] = make_float4(qv.x * kv.x, qv.y * kv.y, qv.z * kv.z, qv.w * kv.w);
+  }
+}
+
+// dk[m] = dA[m, :D] + dA[m, D:] * q[b];   dq[b] (+)= sum_t dA[m, D:] * k[m]   (one thread per (sample, float4 column): fixed order over t)
+__global__ void __launch_bounds__(256) lau_pack_bwd_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ dA,
+                                                          int64_t batch, int32_t T, int32_t D4, int32_t accumulate, float* __restrict__ dq,
+                                                          float* __restrict__ dk) {
+  const int64_t total = batch * D4;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = i / D4;
+    const int c = (int)(i - b * D4);
+    const float4 qv = __ldg(reinterpret_cast<const float4*>(q) + i);
+    float4 acc = accumulate ? reinterpret_cast<const float4*>(dq)[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int t = 0; t < T; ++t) {
+      const int64_t m = b * T + t;
+      const float4 gk = __ldg(reinterpret_cast<const float4*>(dA) + m * 2 * D4 + c);
+      const float4 gm = __ldg(reinterpret_cast<const float4*>(dA) + m * 2 * D4 + D4 + c);
+      const float4 kv = __ldg(reinterpret_cast<const float4*>(k) + m * D4 + c);
+      reinterpret_cast<float4*>(dk)[m * D4 + c] = make_float4(gk.x + gm.x * qv.x, gk.y + gm.y * qv.y, gk.z + gm.z * qv.z, gk.w + gm.w * qv.w);
+      acc.x = fmaf(gm.x, kv.x, acc.x); acc.y = fmaf(gm.y, kv.y, acc.y); acc.z = fmaf(gm.z, kv.z, acc.z); acc.w = fmaf(gm.w, kv.w, acc.w);
+    }
+    reinterpret_cast<float4*>(dq)[i] = acc;
+  }
+}
+
+// out[g, :] = sum_{t < T} x[g*T + t, :]
+__global__ void __launch_bounds__(256) group_sum_kernel(const float* __restrict__ x, int64_t ldx, int64_t groups, int32_t T, int32_t N,
+                                                       float* __restrict__ out) {
+  const int64_t total = groups * N;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t g = i / N;
+    const int n = (int)(i - g * N);
+    float acc = 0.f;
+    for (int t = 0; t < T; ++t) acc += __ldg(x + (g * T + t) * ldx + n);
+    out[i] = acc;
+  }
+}
+
+static inline unsigned lgrid(int64_t n) {
+  int64_t b = (n + 255) / 256;
+  const int64_t cap = (int64_t)sm_count() * 8;
+  return (unsigned)(b > cap ? cap : (b < 1 ? 1 : b));
+}
+
+}  // namespace hrb
+
+HRB_API int hrb_lau_split_weights(const float* w, int64_t ldw, int32_t dim, int32_t units, float* wq, float* wp, float* wpt, void* stream) {
+  HRB_REQUIRE(w && wq && wp && wpt && dim > 0 && units > 0 && ldw >= units, "hrb_lau_split_weights: bad argument");
+  hrb::lau_split_weights_kernel<<<hrb::lgrid((int64_t)dim * units), 256, 0, (cudaStream_t)stream>>>(w, ldw, dim, units, wq, wp, wpt);
+  HRB_LAUNCH_CHECK();
+  return HRB_OK;
+}
+
+HRB_API int hrb_lau_merge_wgrads(const float* dwq, const float* dwp, int32_t dim, int32_t units, float* dw, int64_t ldw, void* stream) {
+  HRB_REQUIRE(dwq && dwp && dw && dim > 0 && units > 0 && ldw >= units, "hrb_lau_merge_wgrads: bad argument");
+  hrb::lau_merge_wgrads_kernel<<<hrb::lgrid((int64_t)dim * units), 256, 0, (cudaStream_t)stream>>>(dwq, dwp, dim, units, dw, ldw);
+  HRB_LAUNCH_CHECK();
+  return HRB_OK;
+}
+
+HRB_API int hrb_lau_pack_fwd(const float* q, const float* k, int64_t batch, int32_t T, int32_t dim, float* out, void* stream) {
+  HRB_REQUIRE(q && k && out && batch >= 0 && T > 0 && dim > 0, "hrb_lau_pack_fwd: bad argument");
+  if (dim % 4 != 0) return hrb::fail(HRB_UNSUPPORTED, "hrb_lau_pack_fwd: dim %d is not a multiple of 4", dim);
+  HRB_REQUIRE(hrb::aligned16(q) && hrb::aligned16(k) && hrb::aligned16(out), "hrb_lau_pack_fwd: buffers must be 16-byte aligned");
+  if (batch == 0) return HRB_OK;
+  hrb::lau_pack_fwd_kernel<<<hrb::lgrid(batch * T * (dim / 4)), 256, 0, (cudaStream_t)stream>>>(q, k, batch * T, T, dim / 4, out);
+  HRB_LAUNCH_CHECK();
+  return HRB_OK;
+}
+
+HRB_API int hrb_lau_pack_bwd(const float* q, const float* k, const float* da, int64_t batch, int32_t T, int32_t dim, int32_t accumulate_dq,
+                             float* dq, float* dk, void* stream) {
+  HRB_REQUIRE(q && k && da && dq && dk && batch >= 0 && T > 0 && dim > 0, "hrb_lau_pack_bwd: bad argument");
+  if (dim % 4 != 0) return hrb::fail(HRB_UNSUPPORTED, "hrb_lau_pack_bwd: dim %d is not a multiple of 4", dim);
+  HRB_REQUIRE(hrb::aligned16(q) && hrb::aligned16(k) && hrb::aligned16(da) && hrb::aligned16(dq) && hrb::aligned16(dk),
+              "hrb_lau_pack_bwd: buffers must be 16-byte aligned");
+  if (batch == 0) return HRB_OK;
+  hrb::lau_pack_bwd_kernel<<<hrb::lgrid(batch * (dim / 4)), 256, 0, (cudaStream_t)stream>>>(q, k, da, batch, T, dim / 4, accumulate_dq, dq, dk);
+  HRB_LAUNCH_CHECK();
+  return HRB_OK;
+}
+
+HRB_API int hrb_group_sum(const float* x, int64_t ldx, int64_t groups, int32_t group_rows, int32_t n, float* out, void* stream) {
+  HRB_REQUIRE(x && out && groups >= 0 && group_rows > 0 && n > 0 && ldx >= n, "hrb_group_sum: bad argument");
+  if (groups == 0) return HRB_OK;
+  hrb::group_sum_kernel<<<hrb::lgrid(groups * n), 256, 0, (cudaStream_t)stream>>>(x, ldx, groups, group_rows, n, out);
+  HRB_LAUNCH_CHECK();
+  return HRB_OK;
+}

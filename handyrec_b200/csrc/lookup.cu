@@ -474,77 +474,6 @@ __global__ void __launch_bounds__(32 * G) lookup_tile_kernel(const FieldDev* __r
 }
 
 // ---------------------------------------------------------------------------------------------
-// (e) sharding helpers
-// ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) shard_ids_kernel(const FieldDev* __restrict__ fields,
-                                                       const int32_t* __restrict__ pos_field, int32_t pos_cols,
-                                                       const int32_t* __restrict__ ids, int64_t ids_ld,
-                                                       int64_t batch, int32_t n_ranks,
-                                                       int32_t* __restrict__ send) {
-  // send[r, b, c] over the dense position columns c (pos space), r = destination rank
-  const int64_t total = batch * pos_cols;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
-       i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t b = i / pos_cols;
-    const int c = (int)(i - b * pos_cols);
-    const FieldDev& f = fields[pos_field[c]];
-    const int32_t id = ids[b * ids_ld + f.ids_col + (c - f.pos_col)];
-    const bool valid = (f.pool == HRB_POOL_NONE || id != 0) && id >= 0;
-    const int owner = valid ? id % n_ranks : -1;
-    const int32_t local = valid ? id / n_ranks : 0;
-    for (int r = 0; r < n_ranks; ++r)
-      send[((int64_t)r * batch + b) * pos_cols + c] = (r == owner) ? local : (int32_t)kNotMine;
-  }
-}
-
-__global__ void __launch_bounds__(256) lookup_combine_kernel(const FieldDev* __restrict__ fields,
-                                                            const int32_t* __restrict__ chunk_field,
-                                                            const int32_t* __restrict__ chunk_q,
-                                                            int32_t n_chunks, int32_t n_fields,
-                                                            const float* __restrict__ psum,
-                                                            const float* __restrict__ pcount, int32_t n_ranks,
-                                                            int64_t batch, int64_t out_ld,
-                                                            float* __restrict__ out,
-                                                            float* __restrict__ inv_count) {
-  const int64_t total = batch * n_chunks;
-  for (int64_t item = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; item < total;
-       item += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t b = item / n_chunks;
-    const int c = (int)(item - b * n_chunks);
-    const int fi = chunk_field[c];
-    const int q = chunk_q[c];
-    const FieldDev& f = fields[fi];
-    float4 acc = f.pool == HRB_POOL_MAX ? make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY)
-                                        : make_float4(0.f, 0.f, 0.f, 0.f);
-    float cnt = 0.f;
-    for (int r = 0; r < n_ranks; ++r) {  // fixed rank order -> deterministic
-      const float4 v = *(reinterpret_cast<const float4*>(psum + ((int64_t)r * batch + b) * out_ld + f.out_col) + q);
-      const float n = pcount[((int64_t)r * batch + b) * n_fields + fi];
-      cnt += n;
-      if (f.pool == HRB_POOL_MAX) {
-        if (n > 0.f) {
-          acc.x = fmaxf(acc.x, v.x); acc.y = fmaxf(acc.y, v.y);
-          acc.z = fmaxf(acc.z, v.z); acc.w = fmaxf(acc.w, v.w);
-        }
-      } else {
-        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
-      }
-    }
-    if (f.pool == HRB_POOL_MEAN) {
-      const float w = cnt > 0.f ? __fdiv_rn(1.0f, cnt) : 0.0f;
-      acc.x *= w; acc.y *= w; acc.z *= w; acc.w *= w;
-    } else if (f.pool == HRB_POOL_MAX && cnt < (float)f.seq_len) {
-      // padded positions: -1e9 (row 0 of a |w|<32 table rounds away), see pooled_chunk
-      acc.x = fmaxf(acc.x, -1e9f); acc.y = fmaxf(acc.y, -1e9f);
-      acc.z = fmaxf(acc.z, -1e9f); acc.w = fmaxf(acc.w, -1e9f);
-    }
-    *(reinterpret_cast<float4*>(out + b * out_ld + f.out_col) + q) = acc;
-    if (inv_count != nullptr && q == 0)
-      inv_count[b * n_fields + fi] = f.pool == HRB_POOL_MEAN ? (cnt > 0.f ? __fdiv_rn(1.0f, cnt) : 0.f) : 1.0f;
-  }
-}
-
-// ---------------------------------------------------------------------------------------------
 // a13 backward.  Step 1: keys.  One thread per (sample, field): key = key_base(table) + id for
 // every valid position, SENTINEL (= total rows, sorts last) for padding; scale = 1/n_valid (mean).
 // ---------------------------------------------------------------------------------------------
@@ -1372,43 +1301,6 @@ HRB_API int hrb_embedding_bwd_dense(const int32_t* ids, int64_t n_ids, const flo
     hot.n_keys = (int32_t)vocab;
   }
   return run_sorted_update(2, w, n_ids, sentinel, key_bits, dim / 4, src, ctx, hot, st);
-}
-
-HRB_API int hrb_shard_ids(const hrb_plan* plan, const int32_t* ids, int64_t ids_ld, int64_t batch, int32_t n_ranks,
-                          int32_t* send, void* stream) {
-  HRB_REQUIRE(plan && ids && send && batch >= 0 && n_ranks > 0, "hrb_shard_ids: null/negative argument");
-  if (batch == 0) return HRB_OK;
-  shard_ids_kernel<<<grid_for(batch * plan->pos_cols, 256), 256, 0, (cudaStream_t)stream>>>(
-      plan->d_fields, plan->d_pos_field, plan->pos_cols, ids, ids_ld, batch, n_ranks, send);
-  HRB_LAUNCH_CHECK();
-  return HRB_OK;
-}
-
-HRB_API int hrb_lookup_partial_fwd(const hrb_plan* plan, const int32_t* local_ids, int64_t ids_ld, int64_t batch,
-                                   float* psum, int64_t out_ld, float* pcount, void* stream) {
-  int rc = check_lookup_args("hrb_lookup_partial_fwd", plan, local_ids, ids_ld, batch, psum, out_ld);
-  if (rc != HRB_OK) return rc;
-  HRB_REQUIRE(pcount != nullptr, "hrb_lookup_partial_fwd: pcount is NULL");
-  if (batch == 0) return HRB_OK;
-  const unsigned grid = grid_for(batch * plan->out_chunks, 256, 8);
-  lookup_items_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(plan->d_fields, plan->d_chunk_field,
-                                                                   plan->d_chunk_q, plan->out_chunks, plan->n_fields,
-                                                                   local_ids, ids_ld, batch, psum, out_ld, pcount,
-                                                                   nullptr);
-  HRB_LAUNCH_CHECK();
-  return HRB_OK;
-}
-
-HRB_API int hrb_lookup_combine(const hrb_plan* plan, const float* psum, const float* pcount, int32_t n_ranks,
-                               int64_t batch, int64_t out_ld, float* out, float* inv_count, void* stream) {
-  HRB_REQUIRE(plan && psum && pcount && out && n_ranks > 0 && batch >= 0, "hrb_lookup_combine: null/negative argument");
-  HRB_REQUIRE(aligned16(psum) && aligned16(out) && out_ld % 4 == 0, "hrb_lookup_combine: buffers must be 16-byte aligned");
-  if (batch == 0) return HRB_OK;
-  lookup_combine_kernel<<<grid_for(batch * plan->out_chunks, 256), 256, 0, (cudaStream_t)stream>>>(
-      plan->d_fields, plan->d_chunk_field, plan->d_chunk_q, plan->out_chunks, plan->n_fields, psum, pcount, n_ranks,
-      batch, out_ld, out, inv_count);
-  HRB_LAUNCH_CHECK();
-  return HRB_OK;
 }
 
 // =============================================================================================

@@ -544,7 +544,9 @@ class DeepFMEngine:
         it = iter(batches)
         losses_host: List[torch.Tensor] = []
         sizes: List[int] = []
-        pool: List[torch.Tensor] = []  # pinned read-back slots are carved from 256-float chunks (one pinned allocation per 256 steps)
+        pool: List[torch.Tensor] = []  # pinned read-back slots are carved from 256-float chunks kept across calls (pinning costs ~1 ms)
+        if getattr(self, "_loss_pool", None) is None:
+            self._loss_pool = []
 
         def upload(slot, batch):
             packed = batch if hasattr(batch, "views") else None  # lowering.HostBatch: a reusable pinned slot
@@ -581,7 +583,10 @@ class DeepFMEngine:
             self._stage_free[cur_slot].record(main)
             k = len(losses_host) % 256
             if k == 0:
-                pool.append(torch.empty(256, dtype=torch.float32).pin_memory())
+                chunk = len(losses_host) // 256
+                if chunk >= len(self._loss_pool):
+                    self._loss_pool.append(torch.empty(256, dtype=torch.float32).pin_memory())
+                pool.append(self._loss_pool[chunk])
             lh = pool[-1][k : k + 1]
             lh.copy_(self.loss_sum, non_blocking=True)  # D2H of this step's loss, not waited for here
             losses_host.append(lh)

@@ -360,6 +360,7 @@ class Model:
 
     @property
     def layers(self) -> List[Layer]:
+        self.sync()
         out, seen = [], set()
         for n in self._order:
             if id(n.layer) not in seen:
@@ -529,7 +530,8 @@ class Model:
                     tot += self.train_on_batch(xb, yb) * nb
                     cnt += nb
                 history["loss"].append(tot / max(cnt, 1))
-            self.sync()
+            # fused training leaves the dense / FM weights in the engine; they are handed back to the layers lazily, the first time
+            # anything reads the layers (`layers`, `get_layer`, `predict` on the layer path, `save_weights`, `sync()`)
             if validation_data is not None:
                 vl, vc = 0.0, 0
                 with torch.no_grad():

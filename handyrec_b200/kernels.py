@@ -219,27 +219,6 @@ class LookupPlan:
         op.bias_corr1, op.bias_corr2 = 1.0 - beta1 ** step, 1.0 - beta2 ** step
         call("hrb_lookup_bwd_update", self._h, _p(ids), ids_ld, B, _p(dout), dout_ld, None, ctypes.byref(op), _p(workspace), workspace.numel(), _stream())
 
-    # (e) sharding helpers --------------------------------------------------------------------
-    def shard_ids(self, ids: torch.Tensor, n_ranks: int) -> torch.Tensor:
-        B = ids.shape[0]
-        send = torch.empty(n_ranks, B, self.pos_cols, device=self.device, dtype=torch.int32)
-        call("hrb_shard_ids", self._h, _p(ids), self._ids_ld(ids), B, n_ranks, _p(send), _stream())
-        return send
-
-    def partial_forward(self, local_ids: torch.Tensor):
-        B = local_ids.shape[0]
-        psum = torch.empty(B, self.out_cols, device=self.device, dtype=torch.float32)
-        pcnt = torch.empty(B, self.n_fields, device=self.device, dtype=torch.float32)
-        call("hrb_lookup_partial_fwd", self._h, _p(local_ids), self._ids_ld(local_ids), B, _p(psum), self.out_cols, _p(pcnt), _stream())
-        return psum, pcnt
-
-    def combine(self, psum: torch.Tensor, pcnt: torch.Tensor, out: Optional[torch.Tensor] = None):
-        n_ranks, B = psum.shape[0], psum.shape[1]
-        if out is None:
-            out = torch.empty(B, self.out_cols, device=self.device, dtype=torch.float32)
-        call("hrb_lookup_combine", self._h, _p(psum), _p(pcnt), n_ranks, B, _row_major_2d(out, "out"), _p(out), None, _stream())
-        return out
-
 
 # --------------------------------------------------------------------------------------------
 # a9 FM

@@ -362,19 +362,7 @@ int hrb_sgd_step(float* param, const float* grad, int64_t n, float lr, float l2_
 
 /* ------------------------------------------------------------------------------------------
  * (e) row-sharded tables: owner(r) = r % n_ranks, local row r / n_ranks  (SURVEY §8e).
- *   bucketize: for ids[B, ids_ld] write, per destination rank, the LOCAL row of every id that rank
- *   owns and 0xFFFFFFFF (= "not yours") elsewhere -- a dense (n_ranks, B, ids_ld) int32 tensor ready for
- *   a fixed-size all-to-all; padding ids (0 in a pooled field) are sent as "not yours".
  * ------------------------------------------------------------------------------------------ */
-int hrb_shard_ids(const hrb_plan* plan, const int32_t* ids, int64_t ids_ld, int64_t batch, int32_t n_ranks,
-                  int32_t* send, void* stream);
-/* owner side: partial pooling of the rows this rank owns: psum[b, out cols] and pcount[b, field]
- * for `batch` = (requesting ranks * their batch) rows of remote ids. */
-int hrb_lookup_partial_fwd(const hrb_plan* plan, const int32_t* local_ids, int64_t ids_ld, int64_t batch,
-                           float* psum, int64_t out_ld, float* pcount, void* stream);
-/* requester side: out = finalise(sum_r psum[r], sum_r pcount[r]) */
-int hrb_lookup_combine(const hrb_plan* plan, const float* psum, const float* pcount, int32_t n_ranks,
-                       int64_t batch, int64_t out_ld, float* out, float* inv_count, void* stream);
 
 /* Compact row exchange (what handyrec_b200/sharded.py runs between NCCL all-to-alls):
  *   requester  hrb_route_ids     owner rank + owner-side key of every position, grouped by owner (stable):

@@ -617,36 +617,6 @@ def test_sigmoid_bce_and_optimisers(dev):
 
 
 # ------------------------------------------------------------------------------------------------
-# (e): row-sharded lookup emulated on one GPU (ranks = loop iterations, no inter-kernel waiting)
-# ------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("n_ranks", [1, 2, 4, 8])
-@pytest.mark.parametrize("pool", ["mean", "sum", "max"])
-def test_sharded_lookup_emulated(dev, n_ranks, pool):
-    k = K()
-    B, D = 257, 16
-    V1, V2 = 1000, 37
-    t1, t2 = rnd(V1, D, seed=1, scale=0.05), rnd(V2, D, seed=2, scale=0.05)
-    g = torch.Generator().manual_seed(5)
-    ids = torch.cat([torch.randint(0, V1, (B, 1), generator=g, dtype=torch.int32), rand_ids(B, 9, V2, seed=6)], 1)
-    fields = [(0, 1, "none", 0, 0), (1, 9, pool, 1, D)]
-    full = k.LookupPlan([t1.to(dev), t2.to(dev)], fields)
-    want = full.forward(ids.to(dev))["out"]
-    send = full.shard_ids(ids.to(dev), n_ranks)  # (n_ranks, B, pos_cols)
-    psums, pcnts = [], []
-    for r in range(n_ranks):
-        shard = k.LookupPlan([t1[r::n_ranks].contiguous().to(dev), t2[r::n_ranks].contiguous().to(dev)], fields)
-        ps, pc = shard.partial_forward(send[r])
-        psums.append(ps)
-        pcnts.append(pc)
-    got = full.combine(torch.stack(psums), torch.stack(pcnts))
-    assert torch.equal(got[:, :D], want[:, :D])  # plain gathers survive the exchange bit-exactly
-    close(got[:, D:], want[:, D:], FWD_TOL if pool != "max" else 1e-4)
-    # and the oracle agrees
-    o = oracle.sharded_lookup_emulated(t2, ids[:, 1:], n_ranks, pool)
-    close(got[:, D:], o[:, 0], FWD_TOL if pool != "max" else 1e-4)
-
-
-# ------------------------------------------------------------------------------------------------
 # a11: BatchNormalization / Dropout inside DNN (layers/core.py:71-73)
 # ------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("shape", [(777, 37), (64, 50, 36), (4096, 128), (3, 5)])

@@ -252,30 +252,22 @@ def main():
     if args.large_table_rows:
         vocabs = [args.large_table_rows if v > args.small_table_rows else v for v in vocabs]
     fields = [(f, 1, "none") for f in range(len(vocabs))]
-    model = None
-    if world == 1:
-        # the reference-shaped call chain: feature groups -> DeepFM(...) -> compile; compile() lowers the graph onto the fused engine
+    # the reference-shaped call chain: feature groups -> DeepFM(...) -> compile; compile() lowers the graph onto the fused engine.
+    # N > 1: the same calls inside `ShardedTables()` -- tables above --small-table-rows are CREATED row-sharded (this rank allocates
+    # rows r % N == rank only, in symmetric memory that peers read over NVLink), the rest replicated; every rank fits its own data
+    import contextlib
+
+    from handyrec_b200 import keras_lite as KL_
+
+    torch.manual_seed(2022)
+    with (KL_.ShardedTables(min_rows=args.small_table_rows) if world > 1 else contextlib.nullcontext()):
         model, KL = build_deepfm_model(vocabs)
         model.dense_table_max_rows = args.small_table_rows
+        model.peer_lookup = not args.no_peer_lookup
         model.compile(optimizer=KL.Adam(learning_rate=1e-3) if args.optimizer == "adam" else KL.SGD(learning_rate=1e-3), loss=KL.binary_crossentropy)
-        assert model._fused is not None, "the DeepFM graph was not lowered onto the fused engine"
-        model._fused.build(B, model.optimizer)
-        eng = model._fused.engine
-    else:
-        # row-sharded tables: this rank holds rows r with r % world == rank (bit-identical to the rows of the full table)
-        from handyrec_b200.sharded import ShardedDeepFMEngine, TorchDistComm
-
-        comm = TorchDistComm()
-        # shards live in symmetric memory (peers map them over NVLink); small tables are replicated in full on every rank
-        tables, peer_ptrs = comm.alloc_tables(vocabs, EMB_DIM, dev, replicate_max_rows=args.small_table_rows)
-        for f, t in enumerate(tables):
-            if vocabs[f] <= args.small_table_rows:
-                K.init_uniform(t, seed=7 + f)
-            else:
-                K.init_uniform(t, seed=7 + f, row_start=rank, row_step=world)
-        eng = ShardedDeepFMEngine(tables, vocabs, fields, N_DENSE, comm, peer_ptrs=None if args.no_peer_lookup else peer_ptrs,
-                                  dnn_hidden_units=DNN_HIDDEN, dnn_activation="relu", batch_size=B, optimizer=args.optimizer, lr=1e-3,
-                                  l2_embd=0.0, seed=2022, replicate_max_rows=args.small_table_rows)
+    assert model._fused is not None, "the DeepFM graph was not lowered onto the fused engine"
+    model._fused.build(B, model.optimizer)
+    eng = model._fused.engine
     if args.bwd_algo != "auto":
         from handyrec_b200 import _lib
         from handyrec_b200._lib import call
@@ -327,7 +319,7 @@ def main():
     launches = launch_count() - l0
 
     # ---- end-to-end through the reference-shaped API ----------------------------------------------
-    if model is not None:
+    if True:
         # (a) Model.fit on a dict of per-feature host arrays (what Keras takes): steps x B samples; per step the host packs the
         # batch (hrb_host_pack_*, background thread), copies it to the device on a copy stream and reads the loss back
         import numpy as np
@@ -357,21 +349,6 @@ def main():
         t0 = time.perf_counter()
         for s in range(args.steps):
             model.train_on_batch(xb, y_host[:B])
-        torch.cuda.synchronize()
-        e2e_sync_ms = (time.perf_counter() - t0) * 1e3
-    else:
-        eng.fit_batches(host[s % NB] for s in range(3))
-        barrier()
-        t0 = time.perf_counter()
-        losses = eng.fit_batches(host[s % NB] for s in range(args.steps))
-        torch.cuda.synchronize()
-        e2e_ms = (time.perf_counter() - t0) * 1e3
-        loss = losses[-1]
-        e2e_api = "ShardedDeepFMEngine.fit_batches (pinned host batches, prefetching copy stream, async loss read-back every step)"
-        barrier()
-        t0 = time.perf_counter()
-        for s in range(args.steps):
-            eng.train_on_batch(*host[s % NB])
         torch.cuda.synchronize()
         e2e_sync_ms = (time.perf_counter() - t0) * 1e3
     clk = clocks.stop()

@@ -242,6 +242,144 @@ def run(args, load_peaks, ClockSampler, WORKLOADS, METRICS):
 
 
 # -------------------------------------------------------------------------------------------------
+def verify_model_api(CRITEO_VOCABS, N_DENSE, EMB_DIM, b, small_rows):
+    """The same comparison through the reference-shaped API: `with ShardedTables(): DeepFM(...).compile(...)` + per-rank `fit(dict)`
+    on N GPUs against ONE single-GPU `DeepFM(...).fit` on the concatenated batches, then a save_weights / load_weights round trip of
+    the sharded model (every rank writes the rows it owns)."""
+    import shutil
+    import tempfile
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from handyrec_b200 import keras_lite as KL
+    from handyrec_b200.features import DenseFeature, FeatureGroup, FeaturePool, SparseFeature
+    from handyrec_b200.layers import CustomEmbedding
+    from handyrec_b200.models import DeepFM
+
+    rank, world = dist.get_rank(), dist.get_world_size()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    vocabs = [max(4, min(v, 300_000)) for v in CRITEO_VOCABS]
+    steps = 3
+
+    def make():
+        sparse = [SparseFeature(f"C{i + 1}", v, EMB_DIM) for i, v in enumerate(vocabs)]
+        dense = [DenseFeature(f"I{i + 1}") for i in range(N_DENSE)]
+        pool = FeaturePool()
+        return DeepFM(FeatureGroup("fm", sparse, pool, l2_embd=0.0), FeatureGroup("dnn", dense + sparse, pool, l2_embd=0.0),
+                      dnn_hidden_units=(64, 32, 1), dnn_activation="relu")
+
+    def data(r):
+        g = np.random.default_rng(1000 + r)
+        x = {f"C{i + 1}": g.integers(0, v, size=(steps * b, 1)).astype(np.int32) for i, v in enumerate(vocabs)}
+        for j in range(N_DENSE):
+            x[f"I{j + 1}"] = g.random((steps * b, 1), dtype=np.float32)
+        return x, (g.random(steps * b) < 0.25).astype(np.float32)
+
+    out = {}
+    for opt in ("sgd", "adam_eps1e-3"):
+        def optimizer():
+            return KL.SGD(learning_rate=0.05) if opt == "sgd" else KL.Adam(learning_rate=1e-3, epsilon=1e-3)
+
+        torch.manual_seed(4321)  # replicated tables / dense weights are broadcast from rank 0 anyway
+        with KL.ShardedTables(min_rows=small_rows, seed=99):
+            model = make()
+            model.compile(optimizer=optimizer(), loss=KL.binary_crossentropy)
+        model._fused.build(b, model.optimizer)
+        model._fused.engine.autotune_embedding_bwd = False
+        emb_layers = [l for l in model._all_layers() if isinstance(l, CustomEmbedding)]
+        # the single-GPU twin on rank 0: same graph, tables assembled from the shards, dense weights copied
+        full = {}
+        for l in emb_layers:
+            w = l.embeddings.data
+            if l._sharded is None:
+                full[l.name] = w.clone()
+                continue
+            rows0 = (l.input_dim + world - 1) // world
+            pad = torch.zeros(rows0, EMB_DIM, device=dev)
+            pad[: w.shape[0]] = w
+            parts = [torch.empty_like(pad) for _ in range(world)]
+            dist.all_gather(parts, pad)
+            t = torch.empty(l.input_dim, EMB_DIM, device=dev)
+            for r in range(world):
+                t[r::world] = parts[r][: t[r::world].shape[0]]
+            full[l.name] = t
+        ref = None
+        if rank == 0:
+            ref = make()
+            for l in ref._all_layers():
+                if isinstance(l, CustomEmbedding):
+                    l.embeddings.data = full[l.name].clone()
+            src = {n: p for n, _, p in _named(model)}
+            for n, lay, p in _named(ref):
+                if not isinstance(lay, CustomEmbedding):
+                    p.data.copy_(src[n].data)
+            ref.dense_table_max_rows = small_rows
+            ref.compile(optimizer=optimizer(), loss=KL.binary_crossentropy)
+            ref._fused.build(b * world, ref.optimizer)
+            ref._fused.engine.autotune_embedding_bwd = False
+        x, y = data(rank)
+        model.fit(x, y, batch_size=b, epochs=1)
+        ls = torch.tensor(model.last_losses, device=dev, dtype=torch.float64)
+        dist.all_reduce(ls)
+        losses_s = (ls / world).tolist()
+        err = {"dense": 0.0, "replicated": 0.0, "sharded": 0.0, "loss": 0.0, "checkpoint": 0.0}
+        if rank == 0:
+            xs, ys = zip(*[data(r) for r in range(world)])
+            xc = {k: np.concatenate([np.concatenate([xr[k][s * b : (s + 1) * b] for xr in xs]) for s in range(steps)]) for k in x}
+            yc = np.concatenate([np.concatenate([yr[s * b : (s + 1) * b] for yr in ys]) for s in range(steps)])
+            ref.fit(xc, yc, batch_size=b * world, epochs=1)
+            err["loss"] = max(abs(a - c) / max(abs(c), 1e-12) for a, c in zip(losses_s, ref.last_losses))
+            ref.sync()
+        model.sync()
+        refw = {n: (lay, p) for n, lay, p in _named(ref)} if rank == 0 else {}
+        for n, lay, p in _named(model):
+            w = p.data
+            if isinstance(lay, CustomEmbedding) and lay._sharded is not None:
+                rows0 = (lay.input_dim + world - 1) // world
+                pad = torch.zeros(rows0, EMB_DIM, device=dev)
+                pad[: w.shape[0]] = w
+                parts = [torch.empty_like(pad) for _ in range(world)]
+                dist.all_gather(parts, pad)
+                if rank == 0:
+                    want_full = refw[n][1].data
+                    for r in range(world):
+                        want = want_full[r::world]
+                        err["sharded"] = max(err["sharded"], float((parts[r][: want.shape[0]] - want).abs().max()) / float(want_full.abs().max()))
+            elif rank == 0:
+                want = refw[n][1].data
+                key = "replicated" if isinstance(lay, CustomEmbedding) else "dense"
+                err[key] = max(err[key], float((w - want).abs().max()) / max(float(want.abs().max()), 1e-12))
+        # checkpoint round trip of the sharded model
+        d = [tempfile.mkdtemp(prefix="hrb_ckpt_") if rank == 0 else None]
+        dist.broadcast_object_list(d, src=0)
+        model.save_weights(d[0])
+        dist.barrier()
+        before = {n: p.data.clone() for n, _, p in _named(model)}
+        for n, _, p in _named(model):
+            p.data.add_(1.0)
+        model.load_weights(d[0])
+        ck = torch.tensor(max(float((p.data - before[n]).abs().max()) for n, _, p in _named(model)), device=dev)
+        dist.all_reduce(ck, op=dist.ReduceOp.MAX)
+        err["checkpoint"] = float(ck)
+        dist.barrier()
+        if rank == 0:
+            shutil.rmtree(d[0], ignore_errors=True)
+            out[f"model_api/{opt}/b{b}"] = {"err": {k: float(f"{v:.3g}") for k, v in err.items()}, "loss_sharded": losses_s,
+                                           "loss_single_gpu": [float(v) for v in ref.last_losses]}
+        del model, ref, full
+        torch.cuda.empty_cache()
+        dist.barrier()
+    return out
+
+
+def _named(model):
+    from handyrec_b200.checkpoint import _named_weights
+
+    return list(_named_weights(model)) if model is not None else []
+
+
 def verify_sharded(args, CRITEO_VOCABS, N_DENSE, EMB_DIM):
     """N>1 correctness on real hardware: 3 steps of the row-sharded engine (symmetric-memory peer lookup, NCCL all-to-all of
     gradient rows, all-reduce of the dense + replicated-table gradients) on per-rank batches == 3 steps of ONE single-GPU engine on
@@ -348,7 +486,9 @@ def verify_sharded(args, CRITEO_VOCABS, N_DENSE, EMB_DIM):
             del eng, ref, tables
             torch.cuda.empty_cache()
             dist.barrier()
+    api = verify_model_api(CRITEO_VOCABS, N_DENSE, EMB_DIM, b_full, small_rows)
     if rank == 0:
+        results.update(api)
         tol = 2e-4
         # pass / fail on the well-conditioned cases; default-eps Adam is reported next to them
         ok = all(max(r["err"].values()) <= tol for k, r in results.items() if not k.startswith("adam/"))

@@ -34,7 +34,7 @@ def _named_weights(model) -> Iterator[Tuple[str, str, torch.nn.Parameter]]:
             if id(p) in seen:
                 continue
             seen.add(id(p))
-            yield f"{i:03d}_{type(layer).__name__}.{key}", layer.name, p
+            yield f"{i:03d}_{type(layer).__name__}.{key}", layer, p
 
 
 def _save_tensor(t: torch.Tensor, base: str, shard_rows: int):
@@ -49,6 +49,12 @@ def _save_tensor(t: torch.Tensor, base: str, shard_rows: int):
         np.save(base + ".npy", t.detach().cpu().numpy())
         files.append(os.path.basename(base) + ".npy")
     return files
+
+
+def _shard_file_names(t: torch.Tensor, base: str, shard_rows: int):
+    if t.dim() == 2 and t.shape[0] > shard_rows:
+        return [os.path.basename(f"{base}.rows{r0:012d}-{min(t.shape[0], r0 + shard_rows):012d}.npy") for r0 in range(0, t.shape[0], shard_rows)]
+    return [os.path.basename(base) + ".npy"]
 
 
 def _load_tensor(dst: torch.Tensor, directory: str, files) -> None:
@@ -71,20 +77,42 @@ def _load_tensor(dst: torch.Tensor, directory: str, files) -> None:
         raise ValueError(f"row shards cover {done} of {dst.shape[0]} rows")
 
 
+def _world(model) -> Tuple[int, int]:
+    comm = getattr(model, "_comm", None)
+    return (comm.rank, comm.N) if comm is not None and comm.N > 1 else (0, 1)
+
+
+def _manifest_name(rank: int, world: int) -> str:
+    return "manifest.json" if world == 1 else f"manifest.rank{rank}of{world}.json"
+
+
 def save_weights(model, directory: str, shard_rows: int = SHARD_ROWS) -> Dict:
+    """Multi-GPU models (keras_lite.ShardedTables): every rank calls this; a row-sharded table is written by each rank as
+    `<key>.rank<r>of<N>...npy` (the rows r % N == rank it owns), replicated weights by rank 0 only, and every rank writes its
+    own manifest.  Loading takes the same N (re-sharding = load on one GPU, save, shard again)."""
     model.sync()  # fused training keeps dense weights in the engine's flat buffer
+    rank, world = _world(model)
     os.makedirs(directory, exist_ok=True)
-    manifest = {"format": "handyrec_b200.weights.v1", "weights": {}}
-    for key, lname, p in _named_weights(model):
-        files = _save_tensor(p.data, os.path.join(directory, key), shard_rows)
-        manifest["weights"][key] = {"layer": lname, "shape": list(p.shape), "files": files}
-    with open(os.path.join(directory, "manifest.json"), "w") as f:
+    manifest = {"format": "handyrec_b200.weights.v1", "world": world, "weights": {}}
+    for key, layer, p in _named_weights(model):
+        sharded = getattr(layer, "_sharded", None) is not None and p is getattr(layer, "embeddings", None)
+        base = os.path.join(directory, key + (f".rank{rank}of{world}" if sharded else ""))
+        if sharded or rank == 0:
+            files = _save_tensor(p.data, base, shard_rows)
+        else:  # rank 0 writes the replicated weights; the names are a pure function of shape and shard_rows
+            files = _shard_file_names(p.data, base, shard_rows)
+        manifest["weights"][key] = {"layer": layer.name, "shape": list(p.shape), "files": files, "row_sharded": bool(sharded)}
+    with open(os.path.join(directory, _manifest_name(rank, world)), "w") as f:
         json.dump(manifest, f, indent=1)
     return manifest
 
 
 def load_weights(model, directory: str) -> None:
-    manifest = json.load(open(os.path.join(directory, "manifest.json")))
+    rank, world = _world(model)
+    path = os.path.join(directory, _manifest_name(rank, world))
+    if not os.path.exists(path):
+        raise FileNotFoundError(f"{path}: no checkpoint for rank {rank} of {world} (saved with another world size?)")
+    manifest = json.load(open(path))
     have = manifest["weights"]
     for key, _, p in _named_weights(model):
         if key not in have:

@@ -25,6 +25,42 @@ def device() -> torch.device:
     return torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu")
 
 
+class ShardedTables:
+    """Creation scope for multi-GPU models (the role of `tf.distribute.Strategy.scope()`), one process per GPU under torch.distributed:
+
+        with ShardedTables():                      # or ShardedTables(comm, min_rows=..., seed=...)
+            model = DeepFM(fm_group, dnn_group, ...)
+            model.compile(Adam(1e-3), binary_crossentropy)
+        model.fit(x_of_this_rank, y_of_this_rank, batch_size=per_rank_batch)
+
+    Embedding tables with more than `min_rows` rows are created row-sharded: this rank allocates and initialises only rows
+    r with r % N == rank (the counter-based initialiser gives every row the value it would have in the full table, so N ranks
+    together hold exactly the table one GPU would have built from the same seed).  Such a table is read by the fused engine
+    only (`compile` lowers the graph onto `ShardedDeepFMEngine`); a graph that does not lower raises instead of running the
+    layer path on a shard.  Smaller tables and dense weights are replicated and broadcast from rank 0 at compile time."""
+
+    active: Optional["ShardedTables"] = None
+
+    def __init__(self, comm=None, min_rows: int = 131072, seed: int = 2022):
+        if comm is None:
+            from .sharded import TorchDistComm
+
+            comm = TorchDistComm()
+        self.comm, self.min_rows, self.seed, self.n_built = comm, int(min_rows), int(seed), 0
+
+    def __enter__(self):
+        ShardedTables.active = self
+        return self
+
+    def __exit__(self, *exc):
+        ShardedTables.active = None
+        return False
+
+    def next_seed(self) -> int:
+        self.n_built += 1
+        return self.seed + 7919 * self.n_built
+
+
 _DTYPES = {"int32": torch.int32, "int64": torch.int64, "float32": torch.float32, "bool": torch.bool, "uint8": torch.uint8}
 
 
@@ -449,14 +485,27 @@ class Model:
                 outs.append(self(xb, training=False).detach().cpu())
         return torch.cat(outs).numpy()
 
-    def compile(self, optimizer=None, loss=None, **kwargs):
+    _comm = None
+
+    def compile(self, optimizer=None, loss=None, distribute=None, **kwargs):
+        """keras.Model.compile.  `distribute` (extra): True under an initialised torch.distributed process group (one process per
+        GPU), or a `handyrec_b200.sharded.TorchDistComm` -- a DeepFM-shaped graph then trains on the row-sharded multi-GPU engine."""
         self.optimizer = optimizer if optimizer is not None else Adam()
         self.loss = loss if loss is not None else binary_crossentropy
         self._fused = None
+        if distribute is None and ShardedTables.active is not None:
+            distribute = ShardedTables.active.comm
+            self.dense_table_max_rows = ShardedTables.active.min_rows
+        if distribute:
+            from .sharded import TorchDistComm
+
+            self._comm = distribute if not isinstance(distribute, bool) else TorchDistComm()
         if self.fuse and self.loss is binary_crossentropy and isinstance(self.optimizer, (Adam, SGD)):
             from .lowering import lower  # a DeepFM-shaped graph runs on the fused engine (one lookup, tcgen05 towers)
 
             self._fused = lower(self)
+        if self._comm is not None and self._comm.N > 1 and self._fused is None:
+            raise ValueError("distribute: only graphs the fused DeepFM engine covers train multi-GPU (lowering.py lists the conditions)")
 
     def train_on_batch(self, x, y) -> float:
         if self._fused is not None and isinstance(x, dict):

@@ -48,15 +48,41 @@ class CustomEmbedding(Layer):
         self.embeddings = None
 
     def build(self, input_shape):
+        from ..keras_lite import ShardedTables
+
         init = None if self._init_weights is None else np.asarray(self._init_weights[0], dtype=np.float32)
-        self.embeddings = self.add_weight("embeddings", (self.input_dim, self.output_dim), initializer="uniform", l2=self.l2, value=init)
+        scope = ShardedTables.active
+        if scope is not None and scope.comm.N > 1 and self.input_dim > scope.min_rows and self.trainable:
+            # row-sharded creation (keras_lite.ShardedTables): only rows r % N == rank exist on this GPU
+            from .. import kernels as K
+            from ..keras_lite import device
+            from ..sharded import shard_rows
+
+            rank, n = scope.comm.rank, scope.comm.N
+            local = torch.empty(shard_rows(self.input_dim, rank, n), self.output_dim, device=device())
+            if init is not None:
+                local.copy_(torch.from_numpy(np.ascontiguousarray(init[rank::n])))
+            else:
+                K.init_uniform(local, seed=scope.next_seed(), row_start=rank, row_step=n)
+            self.embeddings = torch.nn.Parameter(local, requires_grad=True)
+            self._weights["embeddings"] = self.embeddings
+            if self.l2:
+                self._weight_l2["embeddings"] = self.l2
+            self._sharded = (rank, n, self.input_dim)
+        else:
+            self.embeddings = self.add_weight("embeddings", (self.input_dim, self.output_dim), initializer="uniform", l2=self.l2, value=init)
         self.built = True
 
     # Tables with at least this many rows keep their gradient sparse (TF: IndexedSlices) and take the touched-rows-only update
     # (lazy Adam: a declared deviation from Keras' dense Adam step); smaller ones get the dense Keras-exact step.
     SPARSE_UPDATE_MIN_ROWS = 131072
 
+    _sharded = None  # (rank, n_ranks, full rows) when `embeddings` is this rank's row shard
+
     def call(self, inputs):
+        if self._sharded is not None:
+            raise RuntimeError(f"{self.name}: this table is row-sharded over {self._sharded[1]} GPUs; only the fused engine "
+                               "(a DeepFM-shaped model compiled under ShardedTables / distribute=True) reads it")
         ids = inputs.to(torch.int32)
         sink = None
         if self.trainable and self.input_dim >= self.SPARSE_UPDATE_MIN_ROWS and torch.is_grad_enabled() and self.output_dim % 4 == 0:

@@ -15,6 +15,7 @@ memory by `hrb_host_pack_*` (a thread pool inside the library) on a background t
 from __future__ import annotations
 
 import ctypes
+import os
 import queue
 import threading
 from typing import Dict, List, Optional, Sequence, Tuple
@@ -221,6 +222,8 @@ class FusedDeepFM:
         self.ids_cols = sum(f.seq_len for f in spec.fields)
         self._dirty = False
         self._slots: List[HostBatch] = []
+        # packing threads: the host's cores are shared by the ranks of this node (torchrun exports LOCAL_WORLD_SIZE)
+        self._pack_threads = max(1, min(16, (os.cpu_count() or 1) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))))
 
     # ---- engine construction ------------------------------------------------------------------
     def _dense_layers(self):
@@ -242,12 +245,17 @@ class FusedDeepFM:
             return
         self.sync_to_layers()
         dev = torch.device("cuda", torch.cuda.current_device())
-        tabs = [t.embeddings.data.to(dev) for t in self.tables]
         fields = [(next(i for i, t in enumerate(self.tables) if t is f.emb), f.seq_len, f.pool) for f in self.spec.fields]
         dnn = self.spec.dnn
-        eng = DeepFMEngine(tabs, fields, self.n_dense, tuple(dnn.hidden_units), dnn.activation or "linear", batch_size=batch_size, optimizer=opt,
-                           lr=lr, l2_embd=self.spec.fields[0].emb.l2, l2_dnn=float(dnn.l2_reg or 0.0), seed=dnn.seed,
-                           dense_table_max_rows=getattr(self.model, "dense_table_max_rows", 131072))
+        small = getattr(self.model, "dense_table_max_rows", 131072)
+        common = dict(dnn_hidden_units=tuple(dnn.hidden_units), dnn_activation=dnn.activation or "linear", batch_size=batch_size, optimizer=opt,
+                      lr=lr, l2_embd=self.spec.fields[0].emb.l2, l2_dnn=float(dnn.l2_reg or 0.0), seed=dnn.seed)
+        comm = getattr(self.model, "_comm", None)
+        if comm is not None and comm.N > 1:
+            eng = self._build_sharded(comm, dev, fields, small, common)
+        else:
+            tabs = [t.embeddings.data.to(dev) for t in self.tables]
+            eng = DeepFMEngine(tabs, fields, self.n_dense, dense_table_max_rows=small, **common)
         if opt == "adam":
             eng.beta1, eng.beta2, eng.eps = optimizer.b1, optimizer.b2, optimizer.eps
         for i, d in enumerate(self._dense_layers()):
@@ -259,6 +267,42 @@ class FusedDeepFM:
             lay.embeddings.data = eng.tables[t]
         self.engine, self._opt_key = eng, (opt, lr)
         self._slots = []
+
+    def _build_sharded(self, comm, dev, fields, small: int, common: dict):
+        """`compile(..., distribute=True)` under torch.distributed (one process per GPU): tables above `dense_table_max_rows` are
+        row-sharded (row % N, shards in symmetric memory so that peers read them over NVLink), the others replicated; dense
+        parameters are replicated.  Every rank built the model with the SAME seed, so its full-size tables are identical: a
+        sharded table keeps this rank's rows of it and the full copy is released; replicated tables and dense weights are
+        broadcast from rank 0 anyway.  Each rank then fits its own slice of the data (weak scaling, like DistributedDataParallel)."""
+        import torch.distributed as dist
+
+        from .sharded import ShardedDeepFMEngine
+
+        vocabs = [t.input_dim for t in self.tables]
+        D = self.tables[0].output_dim
+        tabs, peer_ptrs = comm.alloc_tables(vocabs, D, dev, replicate_max_rows=small)
+        for t, lay in enumerate(self.tables):
+            cur = lay.embeddings.data.to(dev)
+            if vocabs[t] <= small:
+                if lay._sharded is not None:
+                    raise ValueError(f"{lay.name} was created sharded but dense_table_max_rows={small} asks for a replicated copy")
+                dist.broadcast(cur, src=0, group=comm.group)
+                tabs[t].copy_(cur)
+            elif lay._sharded is not None:  # created under ShardedTables (or a rebuild): already this rank's rows
+                tabs[t].copy_(cur)
+            else:  # a full table built from the same seed on every rank: keep this rank's rows, release the rest
+                tabs[t].copy_(cur[comm.rank :: comm.N])
+                lay._sharded = (comm.rank, comm.N, vocabs[t])
+            lay.embeddings.data = tabs[t]
+            del cur
+        torch.cuda.empty_cache()
+        for d in self._dense_layers():
+            dist.broadcast(d.kernel.data, src=0, group=comm.group)
+            dist.broadcast(d.bias.data, src=0, group=comm.group)
+        dist.broadcast(self.spec.fm.linear.data, src=0, group=comm.group)
+        dist.broadcast(self.spec.fm.w_0.data, src=0, group=comm.group)
+        peer = getattr(self.model, "peer_lookup", True) and all(f[1] == 1 and f[2] in ("none", None) for f in fields)
+        return ShardedDeepFMEngine(tabs, vocabs, fields, self.n_dense, comm, peer_ptrs=peer_ptrs if peer else None, replicate_max_rows=small, **common)
 
     def sync_to_layers(self) -> None:
         """Dense / FM weights live in the engine's flat buffer while it trains; hand them back to the layers."""
@@ -289,10 +333,10 @@ class FusedDeepFM:
         if slot.copied is not None:
             slot.copied.synchronize()  # the previous user's host->device copies have left this pinned slot
         call("hrb_host_pack_i32", id_cols.ptrs, id_cols.dtype, id_cols.width, id_cols.ld, id_cols.n, start, rows,
-             ctypes.c_void_p(slot.ids.data_ptr()), slot.ids.shape[1], 0)
+             ctypes.c_void_p(slot.ids.data_ptr()), slot.ids.shape[1], self._pack_threads)
         if self.n_dense:
             call("hrb_host_pack_f32", dense_cols.ptrs, dense_cols.dtype, dense_cols.width, dense_cols.ld, dense_cols.n, start, rows,
-                 ctypes.c_void_p(slot.dense.data_ptr()), slot.dense.shape[1], 0)
+                 ctypes.c_void_p(slot.dense.data_ptr()), slot.dense.shape[1], self._pack_threads)
         if label_cols is not None:
             call("hrb_host_pack_f32", label_cols.ptrs, label_cols.dtype, label_cols.width, label_cols.ld, 1, start, rows,
                  ctypes.c_void_p(slot.label.data_ptr()), 1, 0)

@@ -293,12 +293,18 @@ class ShardedDeepFMEngine(DeepFMEngine):
             call("hrb_plan_set_peers", self.plan._h, comm.N, ptrs, full)
             self.peer_lookup = True
 
+    _fwd_training = False
+
+    def forward(self, ids, dense, training: bool = False):
+        self._fwd_training = training
+        return super().forward(ids, dense, training)
+
     def _lookup_fm_forward(self, ids, B, st):
         if self.peer_lookup:
             super()._lookup_fm_forward(ids, B, st)
             # the routing needed by the BACKWARD exchange depends on the ids only: it is issued right behind the lookup, on the side
             # stream, so that it fills in beside the dense forward instead of delaying the lookup
-            if self.exchange is not None:
+            if self.exchange is not None and self._fwd_training:
                 main = torch.cuda.current_stream()
                 if self._side is None:
                     self._side = torch.cuda.Stream()

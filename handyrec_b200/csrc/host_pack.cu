@@ -6,12 +6,17 @@
 #include <stdint.h>
 #include <string.h>
 
+#include <atomic>
 #include <condition_variable>
 #include <functional>
 #include <mutex>
 #include <thread>
 #include <type_traits>
 #include <vector>
+
+#if defined(__x86_64__)
+#include <cpuid.h>
+#endif
 
 #include "common.cuh"
 
@@ -77,6 +82,33 @@ Pool& pool() {
 }
 std::mutex g_pack_mu;  // one packing job at a time (the pool is shared)
 
+// Packed batches are read next by the GPU's copy engine over PCIe.  Lines left dirty in the packing cores' private caches make that
+// DMA snoop them out one by one (measured: the last batches of a fit, which no later packing evicts, slowed the step they
+// overlapped by up to 0.8 ms).  Writing every finished block back (clwb / clflushopt) leaves the data in memory for the DMA.
+std::atomic<int> g_writeback{1};
+int cache_writeback_kind() {  // 2 = clwb, 1 = clflushopt, 0 = neither
+  static const int kind = [] {
+#if defined(__x86_64__)
+    unsigned a = 0, b = 0, c = 0, d = 0;
+    if (__get_cpuid_count(7, 0, &a, &b, &c, &d)) return (b & (1u << 24)) ? 2 : ((b & (1u << 23)) ? 1 : 0);
+#endif
+    return 0;
+  }();
+  return kind;
+}
+inline void writeback_range(const void* p, size_t bytes) {
+#if defined(__x86_64__)
+  const int kind = cache_writeback_kind();
+  if (!kind || !g_writeback.load(std::memory_order_relaxed)) return;
+  const char* a = (const char*)((uintptr_t)p & ~(uintptr_t)63);
+  const char* e = (const char*)p + bytes;
+  if (kind == 2) for (; a < e; a += 64) asm volatile(".byte 0x66; xsaveopt %0" : "+m"(*(volatile char*)a));  // clwb
+  else for (; a < e; a += 64) asm volatile(".byte 0x66; clflush %0" : "+m"(*(volatile char*)a));             // clflushopt
+#else
+  (void)p; (void)bytes;
+#endif
+}
+
 template <typename D>
 int pack(const void* const* cols, const int32_t* dtype, const int64_t* width, const int64_t* ld, int32_t n_cols, int64_t row_start,
          int64_t rows, D* dst, int64_t dst_ld, int32_t n_threads) {
@@ -106,7 +138,11 @@ int pack(const void* const* cols, const int32_t* dtype, const int64_t* width, co
           D* d = d0 + c;
           for (int64_t r = r0; r < r1; ++r, d += dst_ld) *d = s[r * l];
         }
+        writeback_range(d0, (size_t)((r1 - r0 - 1) * dst_ld + n_cols) * sizeof(D));
       }
+#if defined(__x86_64__)
+      asm volatile("sfence" ::: "memory");
+#endif
       return;
     }
     for (int64_t r = a; r < b; ++r) {
@@ -122,6 +158,10 @@ int pack(const void* const* cols, const int32_t* dtype, const int64_t* width, co
         d += w;
       }
     }
+    writeback_range(dst + (a - row_start) * dst_ld, (size_t)((b - a) * dst_ld) * sizeof(D));
+#if defined(__x86_64__)
+    asm volatile("sfence" ::: "memory");
+#endif
   };
   if (nt == 1) work(0); else p.run(nt, work);
   return HRB_OK;
@@ -154,4 +194,9 @@ HRB_API int hrb_host_pack_f32(const void* const* cols_host, const int32_t* dtype
   int rc = check("hrb_host_pack_f32", cols_host, dtype_host, width_host, ld_host, n_cols, row_start, rows, dst_host, dst_ld);
   if (rc != HRB_OK) return rc;
   return pack<float>(cols_host, dtype_host, width_host, ld_host, n_cols, row_start, rows, dst_host, dst_ld, n_threads);
+}
+
+HRB_API int hrb_host_pack_set_writeback(int32_t on) {
+  g_writeback.store(on ? 1 : 0);
+  return cache_writeback_kind();
 }

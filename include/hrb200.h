@@ -355,6 +355,11 @@ int hrb_host_pack_i32(const void* const* cols_host, const int32_t* dtype_host, c
 int hrb_host_pack_f32(const void* const* cols_host, const int32_t* dtype_host, const int64_t* width_host, const int64_t* ld_host,
                       int32_t n_cols, int64_t row_start, int64_t rows, float* dst_host, int64_t dst_ld, int32_t n_threads);
 
+/* The packers write every finished block of dst_host back from the CPU caches to memory (x86 clwb / clflushopt), because the
+ * next reader is the GPU's copy engine and dirty lines in the packing cores' private caches slow that DMA.  on = 0 turns the
+ * write-back off (measurements); returns what the CPU offers: 2 clwb, 1 clflushopt, 0 neither (then the call has no effect). */
+int hrb_host_pack_set_writeback(int32_t on);
+
 /* Dense-parameter optimisers on a flat fp32 buffer (Keras Adam / SGD formulas). */
 int hrb_adam_step(float* param, const float* grad, float* m, float* v, int64_t n, float lr, float beta1,
                   float beta2, float eps, float bias_corr1, float bias_corr2, float l2_scale, void* stream);

@@ -210,6 +210,7 @@ def main():
     ap.add_argument("--batch", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-peer-lookup", action="store_true", help="N>1: forward through the all-to-all row exchange instead of NVLink peer loads")
+    ap.add_argument("--no-p2p-grads", action="store_true", help="N>1: move gradient rows with NCCL all-to-alls instead of the fused gather + NVLink store kernel")
     ap.add_argument("--small-table-rows", type=int, default=131072,
                     help="tables up to this many rows take the dense (Keras-exact) optimiser step; at N>1 they are replicated instead of sharded (0 = off)")
     ap.add_argument("--large-table-rows", type=int, default=0, help="C4: give every table above --small-table-rows this many rows (e.g. 100000000 at --gpus 8)")
@@ -264,6 +265,7 @@ def main():
         model, KL = build_deepfm_model(vocabs)
         model.dense_table_max_rows = args.small_table_rows
         model.peer_lookup = not args.no_peer_lookup
+        model.p2p_grad_exchange = not args.no_p2p_grads
         model.compile(optimizer=KL.Adam(learning_rate=1e-3) if args.optimizer == "adam" else KL.SGD(learning_rate=1e-3), loss=KL.binary_crossentropy)
     assert model._fused is not None, "the DeepFM graph was not lowered onto the fused engine"
     model._fused.build(B, model.optimizer)
@@ -452,7 +454,7 @@ def main():
                    "global_batch": B * world, "tables_rows": sum(vocabs), "tables_gb": sum(vocabs) * EMB_DIM * 4 / 1e9, "ids": args.ids,
                    "optimizer": f"{args.optimizer} (dense params and the {n_small} tables of <= {args.small_table_rows} rows, Keras-exact dense step) + {eng.emb_opt} (touched rows of the {n_sharded} large tables)", "l2_embd": 0.0,
                    "l2_flush": "inputs larger than L2 (%.1f GB of tables, rotating pool of 4 batches)" % (sum(vocabs) * EMB_DIM * 4 / 1e9), "scale_vocab": args.scale_vocab,
-                   "parallelism": "single GPU" if world == 1 else f"dp{world}: batch split, {n_sharded} large tables row-sharded (row % {world}), {n_small} small tables replicated (gradients all-reduced with the dense ones), forward = fused lookup+FM reading peer shards over NVLink (symmetric memory), backward = NCCL all-to-all of gradient rows to the owners, all-reduce for dense grads"},
+                   "parallelism": "single GPU" if world == 1 else f"dp{world}: batch split, {n_sharded} large tables row-sharded (row % {world}), {n_small} small tables replicated (gradients all-reduced with the dense ones), forward = fused lookup+FM reading peer shards over NVLink (symmetric memory), backward = " + ("one kernel gathers the gradient rows and stores them into the owners' receive buffers over NVLink (symmetric memory)" if getattr(getattr(eng, "exchange", None), "rx", None) is not None else "NCCL all-to-all of gradient rows to the owners") + ", all-reduce for dense grads"},
         "e2e": {"value": B * world * args.steps / (e2e_ms * 1e-3), "unit": "samples/s", "h2d_bytes_per_step": eng.h2d_bytes_per_step(B), "d2h_bytes_per_step": 4,
                 "ms_per_step": e2e_ms / args.steps, "last_loss": loss, "api": e2e_api,
                 "blocking_train_on_batch_samples_per_s": B * world * args.steps / (e2e_sync_ms * 1e-3)},

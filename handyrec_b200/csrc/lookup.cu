@@ -1464,6 +1464,49 @@ __global__ void __launch_bounds__(256) gather_grads_kernel(const FieldDev* __res
   }
 }
 
+// requester side, backward, fused with the exchange: the gradient row of position perm[j] and its owner-side key are stored
+// straight into the OWNER's receive buffers (peer mappings over NVLink; the local rank's own pointer for its own rows).  Rows for
+// owner d are perm[send_off[d] .. send_off[d+1]) and land at rows dst_off[d].. of d's buffers, i.e. in the layout an all-to-all
+// (ordered by sender) would produce.  Consecutive threads write consecutive 16-byte chunks: 512 contiguous bytes per warp.
+struct PeerScatterArgs {
+  float* grads[HRB_MAX_PEERS];
+  uint32_t* keys[HRB_MAX_PEERS];
+  int64_t send_off[HRB_MAX_PEERS + 1];
+  int64_t dst_off[HRB_MAX_PEERS];
+  int32_t n_ranks;
+};
+
+__global__ void __launch_bounds__(256) scatter_grads_to_owners_kernel(const FieldDev* __restrict__ fields, const int32_t* __restrict__ pos_field,
+                                                                      int32_t pos_cols, int32_t chunks, const int32_t* __restrict__ ids,
+                                                                      int64_t ids_ld, const uint32_t* __restrict__ perm,
+                                                                      const uint32_t* __restrict__ send_keys, int64_t n,
+                                                                      const float* __restrict__ dout, int64_t dout_ld,
+                                                                      const int64_t* __restrict__ full_rows, const PeerScatterArgs a) {
+  const int64_t total = n * chunks;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t j = i / chunks;
+    const int q = (int)(i - j * chunks);
+    int d = 0;
+    while (d + 1 < a.n_ranks && j >= a.send_off[d + 1]) ++d;
+    const int64_t r = a.dst_off[d] + (j - a.send_off[d]);
+    const uint32_t p = __ldg(perm + j);
+    const int64_t b = p / (uint32_t)pos_cols;
+    const int c = (int)(p - (uint32_t)b * (uint32_t)pos_cols);
+    const FieldDev& f = fields[__ldg(pos_field + c)];
+    float s = 1.0f;
+    if (f.pool == HRB_POOL_MEAN) {
+      const int32_t* idp = ids + b * ids_ld + f.ids_col;
+      int cnt = 0;
+      for (int l = 0; l < f.seq_len; ++l) cnt += routed_id_valid(f, idp[l], full_rows);
+      s = cnt > 0 ? __fdiv_rn(1.0f, (float)cnt) : 0.f;
+    }
+    float4 v = __ldg(reinterpret_cast<const float4*>(dout + b * dout_ld + f.out_col) + q);
+    v.x *= s; v.y *= s; v.z *= s; v.w *= s;
+    reinterpret_cast<float4*>(a.grads[d])[r * chunks + q] = v;
+    if (q == 0) a.keys[d][r] = __ldg(send_keys + j);
+  }
+}
+
 }  // namespace hrb
 
 static int route_ws(int64_t n, size_t* cub_bytes, size_t* total) {
@@ -1565,6 +1608,36 @@ HRB_API int hrb_gather_grads(const hrb_plan* plan, const int32_t* ids, int64_t i
   const int chunks = plan->max_dim / 4;
   gather_grads_kernel<<<grid_for(n * chunks, 256), 256, 0, (cudaStream_t)stream>>>(plan->d_fields, plan->d_pos_field, plan->pos_cols, chunks,
                                                                                   ids, ids_ld, perm, n, dout, dout_ld, send, plan->d_full_rows);
+  HRB_LAUNCH_CHECK();
+  return HRB_OK;
+}
+
+HRB_API int hrb_scatter_grads_to_owners(const hrb_plan* plan, const int32_t* ids, int64_t ids_ld, const uint32_t* perm,
+                                        const uint32_t* send_keys, const float* dout, int64_t dout_ld, int32_t n_ranks,
+                                        const int64_t* send_counts_host, const int64_t* dst_off_host, void* const* peer_grads_host,
+                                        void* const* peer_keys_host, void* stream) {
+  HRB_REQUIRE(plan && n_ranks >= 1 && n_ranks <= HRB_MAX_PEERS && send_counts_host && dst_off_host && peer_grads_host && peer_keys_host,
+              "hrb_scatter_grads_to_owners: bad argument");
+  if (!plan->uniform_dim || plan->has_max) return fail(HRB_UNSUPPORTED, "hrb_scatter_grads_to_owners: needs one embedding dim and no max pooling");
+  hrb::PeerScatterArgs a{};
+  a.n_ranks = n_ranks;
+  int64_t n = 0;
+  for (int d = 0; d < n_ranks; ++d) {
+    HRB_REQUIRE(send_counts_host[d] >= 0 && dst_off_host[d] >= 0, "hrb_scatter_grads_to_owners: negative count / offset for rank %d", d);
+    HRB_REQUIRE(send_counts_host[d] == 0 || (peer_grads_host[d] && peer_keys_host[d] && aligned16(peer_grads_host[d])),
+                "hrb_scatter_grads_to_owners: null/misaligned receive buffer of rank %d", d);
+    a.grads[d] = (float*)peer_grads_host[d];
+    a.keys[d] = (uint32_t*)peer_keys_host[d];
+    a.send_off[d] = n;
+    a.dst_off[d] = dst_off_host[d];
+    n += send_counts_host[d];
+  }
+  a.send_off[n_ranks] = n;
+  if (n == 0) return HRB_OK;
+  HRB_REQUIRE(ids && perm && send_keys && dout && aligned16(dout) && dout_ld % 4 == 0, "hrb_scatter_grads_to_owners: null/misaligned pointer");
+  const int chunks = plan->max_dim / 4;
+  hrb::scatter_grads_to_owners_kernel<<<grid_for(n * chunks, 256), 256, 0, (cudaStream_t)stream>>>(
+      plan->d_fields, plan->d_pos_field, plan->pos_cols, chunks, ids, ids_ld, perm, send_keys, n, dout, dout_ld, plan->d_full_rows, a);
   HRB_LAUNCH_CHECK();
   return HRB_OK;
 }

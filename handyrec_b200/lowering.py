@@ -302,7 +302,8 @@ class FusedDeepFM:
         dist.broadcast(self.spec.fm.linear.data, src=0, group=comm.group)
         dist.broadcast(self.spec.fm.w_0.data, src=0, group=comm.group)
         peer = getattr(self.model, "peer_lookup", True) and all(f[1] == 1 and f[2] in ("none", None) for f in fields)
-        return ShardedDeepFMEngine(tabs, vocabs, fields, self.n_dense, comm, peer_ptrs=peer_ptrs if peer else None, replicate_max_rows=small, **common)
+        return ShardedDeepFMEngine(tabs, vocabs, fields, self.n_dense, comm, peer_ptrs=peer_ptrs if peer else None, replicate_max_rows=small,
+                                   p2p_grad_exchange=getattr(self.model, "p2p_grad_exchange", True), **common)
 
     def sync_to_layers(self) -> None:
         """Dense / FM weights live in the engine's flat buffer while it trains; hand them back to the layers."""

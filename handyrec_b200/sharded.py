@@ -87,12 +87,30 @@ class CudaShardProvider:
         call("hrb_gather_grads", self.plan._h, K._p(ids), ids.stride(0), K._p(perm), n, K._p(dout), dout.stride(0), K._p(send), K._stream())
         return send[:n]
 
+    def scatter_grads_to_owners(self, ids, perm, send_keys, dout, send_counts, dst_off, rx: "ReceiveBuffers") -> None:
+        n = self.N
+        call("hrb_scatter_grads_to_owners", self.plan._h, K._p(ids), ids.stride(0), K._p(perm), K._p(send_keys), K._p(dout), dout.stride(0), n,
+             (ctypes.c_int64 * n)(*send_counts), (ctypes.c_int64 * n)(*dst_off), (ctypes.c_void_p * n)(*rx.peer_grads),
+             (ctypes.c_void_p * n)(*rx.peer_keys), K._stream())
+
     def keyed_update(self, keys, grads, n, op: _lib.OptParams):
         need = ctypes.c_size_t(0)
         call("hrb_keyed_bwd_workspace", self.plan._h, n, ctypes.byref(need))
         if self._ws_bwd is None or self._ws_bwd.numel() < need.value:
             self._ws_bwd = torch.empty(int(need.value * 1.25) + 1024, device=self.dev, dtype=torch.uint8)
         call("hrb_keyed_bwd_update", self.plan._h, K._p(keys), K._p(grads), n, ctypes.byref(op), K._p(self._ws_bwd), self._ws_bwd.numel(), K._stream())
+
+
+class ReceiveBuffers:
+    """This rank's receive blocks + the addresses of every rank's blocks as mapped here + the symmetric-memory handle (barriers)."""
+
+    def __init__(self, arena, hdl, grads, keys, peer_grads: List[int], peer_keys: List[int]):
+        self.arena, self.hdl, self.grads, self.keys, self.peer_grads, self.peer_keys = arena, hdl, grads, keys, peer_grads, peer_keys
+
+    def barrier(self, channel: int) -> None:
+        """Cross-GPU barrier on the CURRENT stream (signal pads in symmetric memory, release/acquire at system scope): stores
+        issued to peers by earlier kernels of this stream are visible to kernels the peers launch behind their barrier."""
+        self.hdl.barrier(channel=channel)
 
 
 class TorchDistComm:
@@ -120,8 +138,30 @@ class TorchDistComm:
         work = self.dist.all_to_all_single(recv, send, output_split_sizes=recv_counts, input_split_sizes=send_counts, group=self.group, async_op=True)
         return recv, work.wait
 
+    def all_gather_equal(self, send: torch.Tensor) -> torch.Tensor:
+        """-> (N, len(send)): row r = rank r's `send`."""
+        out = torch.empty((self.N,) + tuple(send.shape), device=send.device, dtype=send.dtype)
+        self.dist.all_gather_into_tensor(out, send.contiguous(), group=self.group)
+        return out
+
     def all_reduce_sum(self, t: torch.Tensor) -> None:
         self.dist.all_reduce(t, group=self.group)
+
+    def alloc_receive_buffers(self, rows: int, dim: int, device) -> Optional["ReceiveBuffers"]:
+        """Owner-side receive buffers of the gradient exchange in symmetric memory: every rank maps every other rank's
+        [rows, dim] fp32 gradient block and [rows] key block and stores into them over NVLink (hrb_scatter_grads_to_owners).
+        None under gloo (CPU tests): the exchange then runs as all-to-alls."""
+        if self.dist.get_backend(self.group) != "nccl":
+            return None
+        import torch.distributed._symmetric_memory as symm_mem
+
+        g_elems = (rows * dim + 63) // 64 * 64
+        arena = symm_mem.empty((g_elems + rows,), dtype=torch.float32, device=device)
+        hdl = symm_mem.rendezvous(arena, group=self.group if self.group is not None else self.dist.group.WORLD)
+        grads = arena[: rows * dim].view(rows, dim)
+        keys = arena[g_elems : g_elems + rows].view(torch.int32)
+        base = [int(p) for p in hdl.buffer_ptrs]
+        return ReceiveBuffers(arena, hdl, grads, keys, base, [b + g_elems * 4 for b in base])
 
     _dense_group = None
 
@@ -164,13 +204,17 @@ class RowExchange:
     def __init__(self, provider, comm):
         self.p, self.comm = provider, comm
         self.N = comm.N
+        self.rx: Optional[ReceiveBuffers] = None  # set -> the backward exchange stores straight into the owners' buffers (no all-to-all)
 
     def route_async(self, ids: torch.Tensor) -> None:
         """Launch the routing of `ids` (owner + key per position, grouped by owner) and the exchange of the per-rank counts;
         nothing waits on the host.  Routing depends on the ids only, so it can run long before its results are needed."""
         self.perm, self.send_keys, counts = self.p.route(ids)
         self._counts_dev = counts
-        self._recv_counts_dev = self.comm.all_to_all_equal(counts[: self.N].contiguous())
+        if self.rx is not None:  # every rank needs the whole N x N count matrix: its write offset at owner d = entries of lower ranks for d
+            self._count_matrix_dev = self.comm.all_gather_equal(counts[: self.N])
+        else:
+            self._recv_counts_dev = self.comm.all_to_all_equal(counts[: self.N].contiguous())
         self._routed = False
         # the routing may have been issued on a side stream: whoever consumes perm / send_keys / the counts first makes ITS
         # stream wait for this event (finish_route), so a caller on another stream never reads them half-written
@@ -184,6 +228,18 @@ class RowExchange:
             return
         if getattr(self, "_route_done", None) is not None:
             torch.cuda.current_stream().wait_event(self._route_done)
+        if self.rx is not None:
+            C = self._count_matrix_dev.tolist()  # the one host sync of the step
+            me = self.comm.rank
+            self.send_counts = [int(x) for x in C[me]]
+            self.recv_counts = [int(C[s][me]) for s in range(self.N)]
+            self.dst_off = [sum(int(C[s][d]) for s in range(me)) for d in range(self.N)]
+            self.n_send, self.n_recv = sum(self.send_counts), sum(self.recv_counts)
+            if self.n_recv > self.rx.keys.shape[0]:
+                raise RuntimeError(f"gradient exchange: {self.n_recv} rows for this owner exceed the receive buffer ({self.rx.keys.shape[0]})")
+            self.recv_keys = None  # keys travel with the gradient rows
+            self._routed = True
+            return
         both = torch.cat([self._counts_dev[: self.N], self._recv_counts_dev]).tolist()  # the one host sync of the step
         self.send_counts, self.recv_counts = [int(x) for x in both[: self.N]], [int(x) for x in both[self.N :]]
         self.n_send, self.n_recv = sum(self.send_counts), sum(self.recv_counts)
@@ -191,6 +247,8 @@ class RowExchange:
         self._routed = True
 
     def forward(self, ids: torch.Tensor, out: torch.Tensor) -> None:
+        if self.rx is not None:
+            raise RuntimeError("the all-to-all forward needs the keys exchanged: do not attach receive buffers in this mode")
         self.route_async(ids)
         self.finish_route()
         rows = self.p.rows_by_key(self.recv_keys, self.n_recv)
@@ -203,6 +261,11 @@ class RowExchange:
         self.finish_route()
         if getattr(self, "_route_done", None) is not None:  # finish_route may have run earlier, on another stream
             torch.cuda.current_stream().wait_event(self._route_done)
+        if self.rx is not None:
+            # fused gather + exchange: one kernel stores rows and keys into the owners' buffers over NVLink
+            self.p.scatter_grads_to_owners(ids, self.perm, self.send_keys, dout, self.send_counts, self.dst_off, self.rx)
+            self._grad_send = self._grad_recv = self._grad_wait = None
+            return
         self._grad_send = self.p.gather_grads(ids, self.perm, self.n_send, dout)
         start = getattr(self.comm, "all_to_all_v_start", None)
         if start is not None:
@@ -211,6 +274,14 @@ class RowExchange:
             self._grad_recv, self._grad_wait = self.comm.all_to_all_v(self._grad_send, self.send_counts, self.recv_counts), None
 
     def backward_finish(self, op, mark=None) -> None:
+        if self.rx is not None:
+            self.rx.barrier(0)  # every rank's stores have landed (and this rank's have left) once all have passed this point
+            if mark is not None:
+                mark("grad_rows_p2p_scatter")
+            self.p.keyed_update(self.rx.keys, self.rx.grads, self.n_recv, op)
+            if mark is not None:
+                mark("keyed_update")
+            return
         if self._grad_wait is not None:
             self._grad_wait()
         if mark is not None:
@@ -241,7 +312,8 @@ class ShardedDeepFMEngine(DeepFMEngine):
     averaged over the global batch.
     """
 
-    def __init__(self, tables, vocabs, fields, n_dense, comm, peer_ptrs=None, replicate_max_rows: int = 0, replicated=None, **kw):
+    def __init__(self, tables, vocabs, fields, n_dense, comm, peer_ptrs=None, replicate_max_rows: int = 0, replicated=None,
+                 p2p_grad_exchange: bool = True, **kw):
         if replicated is None:
             replicated = [t for t, v in enumerate(vocabs) if v <= replicate_max_rows]
         self.replicated = sorted(set(int(t) for t in replicated))
@@ -292,6 +364,9 @@ class ShardedDeepFMEngine(DeepFMEngine):
             full = (ctypes.c_int64 * n_t)(*[int(v) for v in vocabs])
             call("hrb_plan_set_peers", self.plan._h, comm.N, ptrs, full)
             self.peer_lookup = True
+            if p2p_grad_exchange and hasattr(comm, "alloc_receive_buffers"):
+                # worst case for one owner: every position of every rank's batch
+                self.exchange.rx = comm.alloc_receive_buffers(comm.N * self.B * self.plan_shard.pos_cols, self.D, self.dev)
 
     _fwd_training = False
 
@@ -364,8 +439,12 @@ class ShardedDeepFMEngine(DeepFMEngine):
     def _finish_sharded(self, op):
         self.exchange.backward_finish(op, mark=self._mark if self._timeline is not None else None)
         if self.peer_lookup:
-            # peers read this shard in the next forward: nobody may start it before every rank has finished updating
-            self.comm.all_reduce_sum(self._barrier_buf)
+            # peers read this shard in the next forward (and write this rank's receive buffers in the next backward): nobody may
+            # start it before every rank has finished updating
+            if self.exchange.rx is not None:
+                self.exchange.rx.barrier(1)
+            else:
+                self.comm.all_reduce_sum(self._barrier_buf)
 
     def _sync_dense_grads(self):
         if self._rep_done is not None:  # recorded on the side stream when the embedding backward is overlapped

@@ -396,6 +396,18 @@ int hrb_scatter_rows(const hrb_plan* plan, const int32_t* ids, int64_t ids_ld, i
                      const float* rows, float* out, int64_t out_ld, float* pos_rows, void* stream);
 int hrb_gather_grads(const hrb_plan* plan, const int32_t* ids, int64_t ids_ld, const uint32_t* perm, int64_t n,
                      const float* dout, int64_t dout_ld, float* send, void* stream);
+/* hrb_gather_grads fused with the exchange (one node, NVLink): the gradient row and the owner-side key of position perm[j] are
+ * stored directly into the OWNER's receive buffers through peer mappings (symmetric memory) instead of into a local send buffer
+ * that an all-to-all then moves.  perm / send_keys come from hrb_route_ids (grouped by owner); send_counts_host[d] = entries
+ * for owner d, dst_off_host[d] = first row this rank writes in d's buffers (= entries of lower-ranked senders for d, so that
+ * every owner ends up with the layout of an all-to-all ordered by sender); peer_grads_host[d] / peer_keys_host[d] = owner d's
+ * buffers as mapped into this process ([rows, D] fp32 / [rows] uint32; d = own rank: the local pointers).  The caller orders
+ * the stores before the owners' reads with a cross-GPU barrier (sharded.py: symmetric-memory signal barrier). */
+#define HRB_MAX_PEERS 16
+int hrb_scatter_grads_to_owners(const hrb_plan* plan, const int32_t* ids, int64_t ids_ld, const uint32_t* perm,
+                                const uint32_t* send_keys, const float* dout, int64_t dout_ld, int32_t n_ranks,
+                                const int64_t* send_counts_host, const int64_t* dst_off_host, void* const* peer_grads_host,
+                                void* const* peer_keys_host, void* stream);
 int hrb_keyed_bwd_workspace(const hrb_plan* plan, int64_t n, size_t* bytes);
 int hrb_keyed_bwd_update(const hrb_plan* plan, const uint32_t* keys, const float* grads, int64_t n, const hrb_opt_params* opt_host,
                          void* workspace, size_t workspace_bytes, void* stream);

@@ -610,9 +610,11 @@ __device__ __forceinline__ int64_t block_lower_bound(const uint32_t* __restrict_
 // stage 1: CTA (row, slice) reduces its slice of the row's run -> hot_partial[(row*HOT_SLICES + slice)][G*4]
 template <typename GradSrc>
 __global__ void __launch_bounds__(256) bwd_hot_slice_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals,
-                                                           int64_t n, int G, GradSrc src, HotInfo hot, float* __restrict__ hot_partial) {
+                                                           int64_t n, int G, GradSrc src, HotInfo hot, float* __restrict__ hot_partial,
+                                                           const uint32_t* __restrict__ dyn_count) {
   __shared__ float4 red[256];
   const int row = blockIdx.x / HOT_SLICES, slice = blockIdx.x % HOT_SLICES;
+  if (dyn_count != nullptr && (uint32_t)row >= __ldg(dyn_count)) return;  // run-time list: rows past its end do not exist
   const uint32_t key = hot.keys != nullptr ? hot.keys[row] : (uint32_t)row;
   // the row's run [s_lo, s_hi) in the sorted keys: two 256-ary searches by the whole CTA (3 rounds of one load each at n = 1.7 M
   // instead of 2 x 21 dependent loads by one thread)
@@ -658,10 +660,12 @@ __global__ void __launch_bounds__(256) bwd_hot_slice_kernel(const uint32_t* __re
 }
 // stage 2: one group per hot row adds its slices in order and updates the row
 template <int MODE>
-__global__ void __launch_bounds__(256) bwd_hot_apply_kernel(int n_rows, int G, ApplyCtx ctx, HotInfo hot, const float* __restrict__ hot_partial) {
+__global__ void __launch_bounds__(256) bwd_hot_apply_kernel(int n_rows, int G, ApplyCtx ctx, HotInfo hot, const float* __restrict__ hot_partial,
+                                                           const uint32_t* __restrict__ dyn_count) {
   const int gpb = blockDim.x / G;
   const int row = blockIdx.x * gpb + threadIdx.x / G, q = threadIdx.x % G;
   if (threadIdx.x / G >= gpb || row >= n_rows) return;
+  if (dyn_count != nullptr && (uint32_t)row >= __ldg(dyn_count)) return;
   if (hot_partial[(size_t)n_rows * HOT_SLICES * (G * 4) + row] == 0.f) return;  // row not touched by this batch
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
@@ -670,6 +674,43 @@ __global__ void __launch_bounds__(256) bwd_hot_apply_kernel(int n_rows, int G, A
     acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
   }
   apply_row<MODE>(ctx, hot.keys != nullptr ? hot.keys[row] : (uint32_t)row, q, acc);
+}
+
+// Long runs found at run time.  A row whose run in the sorted keys covers two consecutive sample points (every LONG_STEP-th
+// position), i.e. any run of >= 2*LONG_STEP positions and some of LONG_STEP+1..2*LONG_STEP-1, is "long": skewed ids (Zipf
+// histories, popular items) produce runs of 10^4..10^5 positions, whose chunk partials the merge kernel would add one after the
+// other (measured: 2.8 of DIN's 4.9 ms of GPU time per step).  Long rows leave the chunk/merge path like the host-known hot rows
+// above: bwd_long_detect_kernel lists them (one entry per row), HOT_SLICES CTAs per row reduce slices of the run, one group adds
+// the slices in order.  The classification is a pure function of the sorted keys, so every kernel agrees on it.
+constexpr int LONG_STEP = 256;
+struct LongInfo {
+  uint32_t* keys;  // [max] rows found by bwd_long_detect_kernel
+  uint32_t* count; // [1]
+  int32_t max;     // 0: disabled
+};
+// key k at sorted position i (k = keys[i]) -- does its run cover two consecutive sample points?  Only the four sample points
+// around i can be involved: the run contains i, so if it holds two consecutive sample points it holds one next to i.
+__device__ __forceinline__ bool run_is_long(const uint32_t* __restrict__ keys, int64_t n, uint32_t sentinel, int64_t i, uint32_t k) {
+  const int64_t p0 = i / LONG_STEP * LONG_STEP;
+  const uint32_t s0 = __ldg(keys + p0);
+  const uint32_t s1 = p0 + LONG_STEP < n ? __ldg(keys + p0 + LONG_STEP) : sentinel;
+  if (s0 == k && s1 == k) return true;
+  if (s0 == k) return p0 >= LONG_STEP && __ldg(keys + p0 - LONG_STEP) == k;
+  if (s1 == k) return p0 + 2 * LONG_STEP < n && __ldg(keys + p0 + 2 * LONG_STEP) == k;
+  return false;
+}
+
+__global__ void __launch_bounds__(256) bwd_long_detect_kernel(const uint32_t* __restrict__ keys, int64_t n, uint32_t sentinel, HotInfo hot,
+                                                             LongInfo lg) {
+  const int64_t n_pts = (n + LONG_STEP - 1) / LONG_STEP;
+  for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j + 1 < n_pts; j += (int64_t)gridDim.x * blockDim.x) {
+    const uint32_t k = __ldg(keys + j * LONG_STEP);
+    if (k == sentinel || is_hot(hot, k)) continue;
+    if (__ldg(keys + (j + 1) * LONG_STEP) != k) continue;
+    if (j > 0 && __ldg(keys + (j - 1) * LONG_STEP) == k) continue;  // the first pair of the run reports it
+    const uint32_t slot = atomicAdd(lg.count, 1u);
+    if (slot < (uint32_t)lg.max) lg.keys[slot] = k;
+  }
 }
 
 // Step 3: chunk kernel.  G lanes own CH consecutive sorted positions.  Runs (equal keys) that lie
@@ -683,7 +724,8 @@ __global__ void __launch_bounds__(256) bwd_chunk_kernel(const uint32_t* __restri
                                                        const uint32_t* __restrict__ vals, int64_t n,
                                                        uint32_t sentinel, int G, GradSrc src, ApplyCtx ctx,
                                                        float* __restrict__ partial /* (2*chunks, G*4) */,
-                                                       uint32_t* __restrict__ pkey, uint32_t* __restrict__ pflag, HotInfo hot) {
+                                                       uint32_t* __restrict__ pkey, uint32_t* __restrict__ pflag, HotInfo hot,
+                                                       bool long_rows) {
   const int groups_per_block = blockDim.x / G;
   const int q = threadIdx.x % G;
   const int g_in_block = threadIdx.x / G;
@@ -698,6 +740,19 @@ __global__ void __launch_bounds__(256) bwd_chunk_kernel(const uint32_t* __restri
     for (int j = 0; j < CH; ++j) {
       k[j] = (i0 + j < n) ? __ldg(keys + i0 + j) : sentinel;
       if (k[j] != sentinel && is_hot(hot, k[j])) k[j] = sentinel;  // rows of tiny tables belong to bwd_hot_kernel
+    }
+    if (long_rows) {  // positions of long runs belong to the slice kernels (a chunk never straddles a sample block: LONG_STEP % CH == 0)
+      bool lr = false;
+      uint32_t kl = sentinel;
+#pragma unroll
+      for (int j = 0; j < CH; ++j) {
+        if (k[j] == sentinel) continue;
+        if (k[j] != kl) {  // one test per distinct key of the chunk
+          kl = k[j];
+          lr = run_is_long(keys, n, sentinel, i0 + j, kl);
+        }
+        if (lr) k[j] = sentinel;
+      }
     }
 #pragma unroll
     for (int j = 0; j < CH; ++j) {
@@ -808,7 +863,9 @@ static inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a
 
 struct BwdWorkspace {
   uint32_t *keys_in, *keys_out, *vals_in, *vals_out, *pkey, *pflag;
-  float *scale, *partial, *hot_partial;
+  float *scale, *partial, *hot_partial, *long_partial;
+  uint32_t *long_keys, *long_count;
+  int32_t long_max;
   void* cub_tmp;
   size_t cub_bytes;
   size_t total;
@@ -831,6 +888,10 @@ static int carve_bwd_ws(int64_t n, int64_t scale_elems, int max_dim, int key_bit
   w.pkey = (uint32_t*)take((size_t)n_chunks * 2 * 4);
   w.pflag = (uint32_t*)take((size_t)n_chunks * 2 * 4);
   w.hot_partial = (float*)take((size_t)HOT_MAX_RANGES * HOT_MAX_ROWS * (HOT_SLICES * max_dim + 1) * 4);
+  w.long_max = (int32_t)(n / (2 * LONG_STEP) + 2);  // a listed row covers two sample points of its own: at most n / LONG_STEP / 2 rows
+  w.long_keys = (uint32_t*)take((size_t)w.long_max * 4);
+  w.long_count = (uint32_t*)take(4);
+  w.long_partial = (float*)take((size_t)w.long_max * (HOT_SLICES * max_dim + 1) * 4);
   size_t cub_bytes = 0;
   cudaError_t e = cub::DeviceRadixSort::SortPairs(nullptr, cub_bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr,
                                                   (const uint32_t*)nullptr, (uint32_t*)nullptr, (int)n, 0, key_bits);
@@ -877,14 +938,31 @@ static int run_sorted_update(int mode, const BwdWorkspace& w, int64_t n, uint32_
   const unsigned grid1 = grid_for(n_chunks * G, gpb * G, 16);
   const unsigned grid2 = grid_for(2 * n_chunks * G, gpb * G, 16);
   const int launch_threads = gpb * G;
+  // run-time long rows: worth a pass once a run can span two sample points at all
+  const bool long_rows = (G & (G - 1)) == 0 && G <= 128 && n >= 4 * LONG_STEP;
+  LongInfo lg{w.long_keys, w.long_count, long_rows ? w.long_max : 0};
+  HotInfo dyn{};
+  dyn.keys = w.long_keys;
+  dyn.n_keys = w.long_max;
+  if (long_rows) {
+    HRB_CUDA(cudaMemsetAsync(w.long_count, 0, 4, st));
+    bwd_long_detect_kernel<<<grid_for((n + LONG_STEP - 1) / LONG_STEP, 256), 256, 0, st>>>(w.keys_out, n, sentinel, hot, lg);
+    HRB_LAUNCH_CHECK();
+  }
 #define HRB_RUN_MODE(M)                                                                                        \
   bwd_chunk_kernel<M, GradSrc><<<grid1, launch_threads, 0, st>>>(w.keys_out, w.vals_out, n, sentinel, G, src, \
-                                                                 ctx, w.partial, w.pkey, w.pflag, hot);       \
+                                                                 ctx, w.partial, w.pkey, w.pflag, hot, long_rows); \
   HRB_LAUNCH_CHECK();                                                                                          \
   if (hot.n_keys > 0) {                                                                                        \
-    bwd_hot_slice_kernel<GradSrc><<<hot.n_keys * HOT_SLICES, launch_threads, 0, st>>>(w.keys_out, w.vals_out, n, G, src, hot, w.hot_partial); \
+    bwd_hot_slice_kernel<GradSrc><<<hot.n_keys * HOT_SLICES, launch_threads, 0, st>>>(w.keys_out, w.vals_out, n, G, src, hot, w.hot_partial, nullptr); \
     HRB_LAUNCH_CHECK();                                                                                        \
-    bwd_hot_apply_kernel<M><<<(hot.n_keys + gpb - 1) / gpb, launch_threads, 0, st>>>(hot.n_keys, G, ctx, hot, w.hot_partial); \
+    bwd_hot_apply_kernel<M><<<(hot.n_keys + gpb - 1) / gpb, launch_threads, 0, st>>>(hot.n_keys, G, ctx, hot, w.hot_partial, nullptr); \
+    HRB_LAUNCH_CHECK();                                                                                        \
+  }                                                                                                            \
+  if (long_rows) {                                                                                             \
+    bwd_hot_slice_kernel<GradSrc><<<w.long_max * HOT_SLICES, launch_threads, 0, st>>>(w.keys_out, w.vals_out, n, G, src, dyn, w.long_partial, w.long_count); \
+    HRB_LAUNCH_CHECK();                                                                                        \
+    bwd_hot_apply_kernel<M><<<(w.long_max + gpb - 1) / gpb, launch_threads, 0, st>>>(w.long_max, G, ctx, dyn, w.long_partial, w.long_count); \
     HRB_LAUNCH_CHECK();                                                                                        \
   }                                                                                                            \
   bwd_merge_kernel<M><<<grid2, launch_threads, 0, st>>>(n_chunks, G, ctx, w.partial, w.pkey, w.pflag);         \

@@ -479,10 +479,13 @@ class Model:
         n = len(next(iter(x.values()))) if isinstance(x, dict) else len(x[0] if isinstance(x, (list, tuple)) else x)
         bs = batch_size or n
         outs = []
+        from .kernels import deferred_id_checks
+
         with torch.no_grad():
             for s in range(0, n, bs):
                 xb = {k: v[s : s + bs] for k, v in x.items()} if isinstance(x, dict) else [v[s : s + bs] for v in x]
-                outs.append(self(xb, training=False).detach().cpu())
+                with deferred_id_checks():
+                    outs.append(self(xb, training=False).detach().cpu())
         return torch.cat(outs).numpy()
 
     _comm = None
@@ -513,6 +516,12 @@ class Model:
             self._fused.build(n, self.optimizer)
             return self._fused.train_on_batch(x, y) + self._fused.reg_loss()
         self.sync()
+        from .kernels import deferred_id_checks
+
+        with deferred_id_checks():  # the lookups' out-of-range flags are read once, with the loss, instead of one host sync per lookup
+            return self._train_on_batch_layers(x, y)
+
+    def _train_on_batch_layers(self, x, y) -> float:
         out = self(x, training=True)
         yt = torch.as_tensor(np.asarray(y), dtype=torch.float32).to(device()) if not isinstance(y, torch.Tensor) else y.to(device())
         loss = self.loss(yt, out)

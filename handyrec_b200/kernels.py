@@ -52,10 +52,36 @@ def init_uniform(table: torch.Tensor, seed: int, lo: float = -0.05, hi: float = 
     return table
 
 
+_oob_pending: Optional[list] = None  # a list while a `deferred_id_checks()` block is open
+
+
 def _raise_if_oob(oob: torch.Tensor, what: str) -> None:
+    if _oob_pending is not None:
+        _oob_pending.append((oob, what))
+        return
     flag = oob.tolist()
     if flag[0]:
         raise IndexError(f"{what}: id out of range (near flat sample index {flag[1]})")
+
+
+class deferred_id_checks:
+    """Reading a lookup's out-of-range flag is a host sync.  Inside this block the flags of all lookups are collected and read
+    together when the block closes (one sync, normally shared with the step's loss read-back); an out-of-range id still raises
+    IndexError from the same user call, only after the step's kernels have been issued (such a position reads as a zero row)."""
+
+    def __enter__(self):
+        global _oob_pending
+        self.prev, _oob_pending = _oob_pending, []
+        return self
+
+    def __exit__(self, et, ev, tb):
+        global _oob_pending
+        pending, _oob_pending = _oob_pending, self.prev
+        if et is None and pending:
+            for flag, (_, what) in zip(torch.stack([o for o, _ in pending]).tolist(), pending):
+                if flag[0]:
+                    raise IndexError(f"{what}: id out of range (near flat sample index {flag[1]})")
+        return False
 
 
 # --------------------------------------------------------------------------------------------
@@ -203,8 +229,8 @@ class LookupPlan:
 
     def backward_update(self, ids: torch.Tensor, dout: torch.Tensor, opt: str = "sgd", lr: float = 0.01, l2_scale: float = 0.0,
                         beta1: float = 0.9, beta2: float = 0.999, eps: float = 1e-7, step: int = 1,
-                        workspace: Optional[torch.Tensor] = None) -> None:
-        """Sort -> segment-reduce -> update the touched rows of every table in place."""
+                        workspace: Optional[torch.Tensor] = None, autotune: bool = False) -> None:
+        """Segment-reduce the gradient rows per table row and update the touched rows of every table in place."""
         B = ids.shape[0]
         ids_ld = self._ids_ld(ids)
         dout_ld = _row_major_2d(_chk(dout, torch.float32, "dout", contiguous=False), "dout")
@@ -217,7 +243,41 @@ class LookupPlan:
         op.opt = _lib.OPT_SGD if opt == "sgd" else _lib.OPT_ADAM_LAZY
         op.lr, op.beta1, op.beta2, op.eps, op.l2_scale = lr, beta1, beta2, eps, l2_scale
         op.bias_corr1, op.bias_corr2 = 1.0 - beta1 ** step, 1.0 - beta2 ** step
+        trial = self._next_bwd_trial(B) if autotune else None
+        if trial is not None:
+            call("hrb_plan_set_bwd_algo", self._h, _lib.BWD_UNITS if trial == "units" else _lib.BWD_SORT)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
         call("hrb_lookup_bwd_update", self._h, _p(ids), ids_ld, B, _p(dout), dout_ld, None, ctypes.byref(op), _p(workspace), workspace.numel(), _stream())
+        if trial is not None:
+            e1.record()
+            e1.synchronize()
+            self._finish_bwd_trial(trial, e0.elapsed_time(e1))
+
+    # Which implementation of the backward is faster depends on the ids (uniform: the partition path; a few rows collecting most
+    # positions: the sorted path with its run-time long-row pass).  With autotune=True calls 3..6 of a plan at one batch size time
+    # both (two trials each, one host sync per trial) and the faster one is kept; both give the same result to rounding.
+    _bwd_trial_log = None
+    bwd_algo = "auto"
+
+    def _next_bwd_trial(self, B: int) -> Optional[str]:
+        if self.bwd_algo != "auto":
+            return None
+        if self._bwd_trial_log is None or self._bwd_trial_log["B"] != B:
+            self._bwd_trial_log = {"B": B, "calls": 0, "units": [], "sort": []}
+        log = self._bwd_trial_log
+        log["calls"] += 1
+        if log["calls"] <= 2:
+            return None
+        return "units" if len(log["units"]) <= len(log["sort"]) else "sort"
+
+    def _finish_bwd_trial(self, trial: str, ms: float) -> None:
+        log = self._bwd_trial_log
+        log[trial].append(ms)
+        if len(log["units"]) >= 2 and len(log["sort"]) >= 2:
+            self.bwd_algo = "units" if min(log["units"]) <= min(log["sort"]) else "sort"
+            self.bwd_algo_ms = {"units": min(log["units"]), "sort": min(log["sort"])}
+            call("hrb_plan_set_bwd_algo", self._h, _lib.BWD_UNITS if self.bwd_algo == "units" else _lib.BWD_SORT)
 
 
 # --------------------------------------------------------------------------------------------

@@ -113,9 +113,9 @@ class CustomEmbedding(Layer):
             self._plan = K.LookupPlan([w], [(0, 1, "none", 0, 0)], [self._m] if adam else None, [self._v] if adam else None)
         if adam:
             self._plan.backward_update(ids, rows, opt="adam", lr=optimizer.lr, l2_scale=2.0 * self.l2, beta1=optimizer.b1, beta2=optimizer.b2,
-                                       eps=optimizer.eps, step=max(optimizer.t, 1))
+                                       eps=optimizer.eps, step=max(optimizer.t, 1), autotune=True)
         else:
-            self._plan.backward_update(ids, rows, opt="sgd", lr=optimizer.lr, l2_scale=2.0 * self.l2)
+            self._plan.backward_update(ids, rows, opt="sgd", lr=optimizer.lr, l2_scale=2.0 * self.l2, autotune=True)
 
     def compute_mask(self, inputs, mask=None):
         if not self.mask_zero:  # tools.py:94-95

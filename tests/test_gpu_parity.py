@@ -322,6 +322,28 @@ def test_embedding_bwd_dense(dev, V, D, n):
     assert torch.equal(got0, k.embedding_bwd_dense(ids.to(dev), dout.to(dev), V))
 
 
+@pytest.mark.parametrize("V,D,n,dist", [(3953, 32, 204800, "zipf"), (1000, 16, 50000, "one"), (300000, 64, 120000, "zipf"), (5000, 8, 3000, "two")])
+def test_embedding_bwd_dense_long_runs(dev, V, D, n, dist):
+    """Skewed ids put 10^3..10^5 positions on one row: those runs leave the chunk/merge chain for the run-time long-row pass
+    (lookup.cu: bwd_long_detect_kernel + slice kernels).  Same sums as index_add, bit-reproducible."""
+    k = K()
+    if dist == "zipf":
+        ids = _zipf_ids(n, V, 1.05, 5)
+    elif dist == "one":
+        ids = torch.full((n,), 7, dtype=torch.int32)
+        ids[::9] = 8
+    else:  # two runs of 257..511 positions (the boundary of the classification) between short ones
+        g = torch.Generator().manual_seed(1)
+        ids = torch.randint(0, V, (n,), generator=g, dtype=torch.int32)
+        ids[:300] = 11
+        ids[300:811] = 12
+    dout = rnd(n, D, seed=V, scale=1.0 / 64)
+    want = oracle.embedding_grad_dense(V, ids, dout)
+    got = k.embedding_bwd_dense(ids.to(dev), dout.to(dev), V)
+    close(got, want, GRAD_TOL)
+    assert torch.equal(got, k.embedding_bwd_dense(ids.to(dev), dout.to(dev), V))
+
+
 @pytest.mark.parametrize("pool", ["mean", "sum"])
 @pytest.mark.parametrize("opt", ["sgd", "adam"])
 def test_group_lookup_bwd_update(dev, pool, opt):
@@ -406,9 +428,10 @@ def _zipf_ids(B, V, a, seed):
     return x.long().clamp_(1, V - 1).to(torch.int32)
 
 
+@pytest.mark.parametrize("algo", ["units", "sort"])
 @pytest.mark.parametrize("opt", ["sgd", "adam"])
 @pytest.mark.parametrize("B,dist", [(65536, "zipf"), (30001, "uniform"), (65536, "onehot")])
-def test_group_lookup_bwd_unit_path_skew(dev, opt, B, dist):
+def test_group_lookup_bwd_unit_path_skew(dev, opt, B, dist, algo):
     """The sort-free backward (embedding_bwd.cu) under skew: Zipf ids (histogram splits, single hot rows inside big tables),
     one id for the whole batch (a row with 65536 positions), tiny tables (slices), a batch that is not a multiple of 16;
     a dense-updated table next to in-place ones; deterministic bit for bit."""
@@ -435,6 +458,9 @@ def test_group_lookup_bwd_unit_path_skew(dev, opt, B, dist):
         plan = k.LookupPlan(dt, fields, adam_m=ms, adam_v=vs)
         dense_g = torch.zeros_like(dt[3])
         plan.set_dense_grads([None, None, None, dense_g, None, None])  # table 3 is "dense-updated": gradient sums only
+        from handyrec_b200 import _lib
+
+        _lib.call("hrb_plan_set_bwd_algo", plan._h, _lib.BWD_UNITS if algo == "units" else _lib.BWD_SORT)
         plan.backward_update(ids.to(dev), dout.to(dev), opt=opt, lr=lr, step=1)
         torch.cuda.synchronize()
         return dt, dense_g

@@ -21,7 +21,14 @@ __all__ = [
 ]
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def _stream() -> ctypes.c_void_p:
+    """The current torch stream of the current device as a raw cudaStream_t (called once per kernel launch: the raw getter
+    costs ~0.3 us against ~8 us for building a torch.cuda.Stream object)."""
+    if _raw_stream is not None:
+        return ctypes.c_void_p(_raw_stream(torch.cuda.current_device()))
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
@@ -341,7 +348,7 @@ def dense_bwd_w(x: torch.Tensor, dz: torch.Tensor, dw: Optional[torch.Tensor] = 
     N = dz.shape[1]
     need = ctypes.c_size_t(0)
     call("hrb_dense_bwd_w_workspace", M, K, N, ctypes.byref(need))
-    key = (x.device.index, torch.cuda.current_stream().cuda_stream)
+    key = (x.device.index, _stream().value)
     ws = _dense_ws.get(key)
     if ws is None or ws.numel() < need.value:
         ws = torch.empty(need.value, device=x.device, dtype=torch.uint8)
@@ -471,7 +478,7 @@ def dense_bwd_w_t(xt, dzt, dz=None, dw=None, dbias=None):
     N = dzt.shape[0]
     need = ctypes.c_size_t(0)
     call("hrb_dense_bwd_w_t_workspace", M, Kd, N, ctypes.byref(need))
-    key = ("t", xt.device.index, torch.cuda.current_stream().cuda_stream)
+    key = ("t", xt.device.index, _stream().value)
     ws = _dense_ws.get(key)
     if ws is None or ws.numel() < need.value:
         ws = torch.empty(need.value, device=xt.device, dtype=torch.uint8)
@@ -491,7 +498,7 @@ def dense_bwd_w_xn(x, dzt, dw=None, want_bias=True):
     N = dzt.shape[0]
     need = ctypes.c_size_t(0)
     call("hrb_dense_bwd_w_t_workspace", M, Kd, N, ctypes.byref(need))
-    key = ("t", x.device.index, torch.cuda.current_stream().cuda_stream)
+    key = ("t", x.device.index, _stream().value)
     ws = _dense_ws.get(key)
     if ws is None or ws.numel() < need.value:
         ws = torch.empty(need.value, device=x.device, dtype=torch.uint8)

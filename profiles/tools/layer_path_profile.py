@@ -45,4 +45,5 @@ for s in range(8):
     model.train_on_batch(*pool[s % 4])
 torch.cuda.synchronize()
 pr.disable()
-pstats.Stats(pr).sort_stats("tottime").print_stats(30)
+pstats.Stats(pr).sort_stats("tottime").print_stats(25)
+pstats.Stats(pr).sort_stats("cumulative").print_stats(60)

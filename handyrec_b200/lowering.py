@@ -223,7 +223,8 @@ class FusedDeepFM:
         self._dirty = False
         self._slots: List[HostBatch] = []
         # packing threads: the host's cores are shared by the ranks of this node (torchrun exports LOCAL_WORLD_SIZE)
-        self._pack_threads = max(1, min(16, (os.cpu_count() or 1) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))))
+        cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+        self._pack_threads = max(1, min(16, cores // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))))
 
     # ---- engine construction ------------------------------------------------------------------
     def _dense_layers(self):

@@ -32,11 +32,18 @@ def short(name):
 
 
 def launches(path, steps):
-    rows = read_ncu_csv(path)
+    rows = [r for r in read_ncu_csv(path) if r.get("Metric Name") == "gpu__time_duration.sum"]
+    if steps == "auto":
+        # steps only: drop the set-up kernels before the first step's first kernel (pack_dense) and the trailing partial step
+        # (after the last dense-optimiser launch); one sigmoid_bce launch per step
+        first = next((i for i, r in enumerate(rows) if "pack_dense_kernel" in r["Kernel Name"]), 0)
+        last = max((i for i, r in enumerate(rows) if "adam_kernel" in r["Kernel Name"] or "sgd_kernel" in r["Kernel Name"]), default=len(rows) - 1)
+        rows = rows[first : last + 1]
+        steps = max(1, sum(1 for r in rows if "sigmoid_bce_kernel" in r["Kernel Name"]))
+        print(f"{steps} training steps captured (set-up kernels before the first step and the trailing partial step dropped)\n")
+    steps = float(steps)
     agg = OrderedDict()
     for r in rows:
-        if r.get("Metric Name") != "gpu__time_duration.sum":
-            continue
         v = float(r["Metric Value"].replace(",", ""))
         unit = r.get("Metric Unit", "ns")
         us = v / 1e3 if unit.startswith("n") else (v if unit.startswith("u") else v * 1e3)
@@ -123,7 +130,7 @@ if __name__ == "__main__":
         to_json(sys.argv[2], sys.argv[3])
         raise SystemExit(0)
     if len(sys.argv) >= 4 and sys.argv[1] == "launches":
-        launches(sys.argv[2], float(sys.argv[3]))
+        launches(sys.argv[2], sys.argv[3] if len(sys.argv) > 3 else "auto")
     elif len(sys.argv) >= 3 and sys.argv[1] == "full":
         full(sys.argv[2])
     else:

@@ -58,16 +58,23 @@ def load_traffic(kernel_key: str):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    """nvidia-smi clocks / throttle reasons sampled every 100 ms; samples count from mark() (start of the timed steps) to stop()."""
 
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
-    def __init__(self, index: int):
-        self.index, self.proc, self.lines = index, None, []
+    def __init__(self, index):
+        """index: one GPU index or a list of them (rank 0 of a multi-GPU run samples every GPU of the job from ONE nvidia-smi process:
+        eight of them starting up beside the timed region -- NVML initialisation walks all GPUs -- perturbed the launches)."""
+        self.index = ",".join(str(i) for i in index) if isinstance(index, (list, tuple, range)) else str(index)
+        self.proc, self.lines, self.first = None, [], 0
+
+    def mark(self):
+        """Samples from here on count (call at the start of the timed region; the process was started earlier)."""
+        self.first = len(self.lines)
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", self.index, f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=lambda: [self.lines.append(l) for l in self.proc.stdout], daemon=True)
             self.t.start()
@@ -85,7 +92,7 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for l in self.lines:
+        for l in self.lines[self.first:]:
             f = [x.strip() for x in l.split(",")]
             if len(f) < 7:
                 continue
@@ -97,7 +104,9 @@ class ClockSampler:
             for n, v in zip(names, f[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(n)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_min_mhz": min(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm), "gpus": self.index,
+                "window": "from the start of the timed steps to the end of the end-to-end runs (GPU under load throughout)"}
 
 
 # -------------------------------------------------------------------------------------------------
@@ -246,6 +255,11 @@ def main():
 
         return bench_models.verify_sharded(args, CRITEO_VOCABS, N_DENSE, EMB_DIM)
     peaks = load_peaks()
+    # ONE nvidia-smi process (rank 0) samples every GPU of the job; it is started here, seconds before the timed region, so that its
+    # start-up (NVML walks all GPUs) is over when the timing begins -- samples count from ClockSampler.mark() on
+    clocks = ClockSampler(list(range(world))) if rank == 0 else None
+    if clocks is not None:
+        clocks.start()
 
     # ---- workload -------------------------------------------------------------------------------
     B = args.batch or BATCH
@@ -308,8 +322,8 @@ def main():
         eng.train_step_on_device(ids_pool[s % NB], dense_pool[s % NB], label_pool[s % NB])
     barrier()
     l0 = launch_count()
-    clocks = ClockSampler(local_rank)
-    clocks.start()
+    if clocks is not None:
+        clocks.mark()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
@@ -353,7 +367,7 @@ def main():
             model.train_on_batch(xb, y_host[:B])
         torch.cuda.synchronize()
         e2e_sync_ms = (time.perf_counter() - t0) * 1e3
-    clk = clocks.stop()
+    clk = clocks.stop() if clocks is not None else None
 
     if world > 1:
         import torch.distributed as dist

@@ -176,6 +176,8 @@ def run(args, load_peaks, ClockSampler, WORKLOADS, METRICS):
     torch.cuda.set_device(0)
     dev = torch.device("cuda", 0)
     peaks = load_peaks()
+    clocks = ClockSampler(0)  # started before the model is built: its start-up is over when the timing begins; samples count from mark()
+    clocks.start()
     wl = args.workload
     if wl == "din":
         B = args.batch or DIN_B
@@ -194,8 +196,7 @@ def run(args, load_peaks, ClockSampler, WORKLOADS, METRICS):
     for s in range(max(args.warmup, 3)):
         model.train_on_batch(*pool_dev[s % NB])
     torch.cuda.synchronize()
-    clocks = ClockSampler(0)
-    clocks.start()
+    clocks.mark()
     l0 = launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()

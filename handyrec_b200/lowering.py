@@ -224,7 +224,8 @@ class FusedDeepFM:
         self._slots: List[HostBatch] = []
         # packing threads: the host's cores are shared by the ranks of this node (torchrun exports LOCAL_WORLD_SIZE)
         cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-        self._pack_threads = max(1, min(16, cores // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))))
+        ranks = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))
+        self._pack_threads = max(1, min(16, cores // ranks - (1 if ranks > 1 else 0)))  # leave a core to the rank's launching thread
 
     # ---- engine construction ------------------------------------------------------------------
     def _dense_layers(self):

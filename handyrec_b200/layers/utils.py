@@ -11,27 +11,14 @@ from .core import get_activation_layer  # noqa: F401  (same import location as t
 
 
 class Concatenate(Layer):
-    """keras Concatenate.  Adjacent column slices of one fused lookup buffer are recognised and returned without a copy."""
+    """keras Concatenate.  (The zero-copy form of this concat is the fused engine's layout contract, DESIGN.md 2: `lowering.py` puts
+    DeepFM-shaped graphs there; on the layer path it is a plain copy.)"""
 
     def __init__(self, axis=-1, **kw):
         super().__init__(**kw)
         self.axis = axis
 
     def call(self, inputs):
-        views = [getattr(t, "_fused_view", None) for t in inputs]
-        if all(v is not None for v in views) and self.axis in (-1, 2, 1):
-            buf = views[0][0]
-            cols = [v[1] for v in views]
-            same = all(v[0] is buf for v in views)
-            adjacent = all(cols[i][1] == cols[i + 1][0] for i in range(len(cols) - 1))
-            if same and adjacent:
-                B, D = buf.shape[0], inputs[0].shape[-1]
-                block = buf[:, cols[0][0] : cols[-1][1]]
-                if self.axis == 1 and all(t.shape[-1] == D for t in inputs):
-                    out = block.unflatten(1, (len(inputs), D))      # (B, F, D): the FM input, zero-copy
-                    return out
-                if self.axis in (-1, 2):
-                    return block.unsqueeze(1)                        # (B, 1, sum D): zero-copy
         return torch.cat(list(inputs), dim=self.axis)
 
     def compute_output_shape(self, input_shape):

@@ -456,7 +456,7 @@ def main():
               "traffic": b_traffic, "traffic_note": b_note}
 
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:  # the CPU arm is timed at N=1 only (the N>1 lines carry cpu_baseline: null)
         r = cpu_deepfm_arm(batch=B, vocab_cap=CPU_VOCAB_CAP, steps=3, warmup=1)
         cpu = {"value": r["samples_per_s"], "unit": "samples/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]}
 

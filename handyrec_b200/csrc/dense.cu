@@ -220,6 +220,61 @@ static inline void launch_split_reduce(const float* part, int64_t rows, int32_t 
   }
 }
 
+// Two reductions with the same split count in ONE launch (weight-gradient partials + bias-gradient partials of a layer): the first
+// a.blocks CTAs work on job a, the rest on job b, each with the scheme launch_split_reduce would have picked for it alone, so every
+// output element is summed in exactly the same order as by two separate launches.
+struct ReduceJob {
+  const float* part;
+  int64_t rows;
+  int32_t cols;
+  int64_t ld_part;
+  float* out;
+  int64_t ld_out;
+  int32_t wide;
+  int32_t blocks;
+};
+__global__ void __launch_bounds__(256) split_reduce2_kernel(const ReduceJob a, const ReduceJob b, int32_t splits) {
+  const bool first = (int)blockIdx.x < a.blocks;
+  const ReduceJob& j = first ? a : b;
+  const int64_t bid = first ? blockIdx.x : blockIdx.x - a.blocks;
+  const int64_t total = j.rows * j.cols;
+  if (!j.wide) {
+    for (int64_t i = bid * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)j.blocks * blockDim.x) {
+      const int64_t r = i / j.cols;
+      const int c = (int)(i - r * j.cols);
+      float s = 0.f;
+      for (int z = 0; z < splits; ++z) s += j.part[((int64_t)z * j.rows + r) * j.ld_part + c];
+      j.out[r * j.ld_out + c] = s;
+    }
+    return;
+  }
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (bid * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)j.blocks * blockDim.x) >> 5;
+  for (int64_t i = warp0; i < total; i += nwarps) {
+    const int64_t r = i / j.cols;
+    const int c = (int)(i - r * j.cols);
+    float s = 0.f;
+    for (int z = lane; z < splits; z += 32) s += __ldg(j.part + ((int64_t)z * j.rows + r) * j.ld_part + c);
+    s = warp_sum(s);
+    if (lane == 0) j.out[r * j.ld_out + c] = s;
+  }
+}
+static inline ReduceJob reduce_job(const float* part, int64_t rows, int32_t cols, int64_t ld_part, int32_t splits, float* out, int64_t ld_out) {
+  const int64_t total = rows * cols;
+  ReduceJob j{part, rows, cols, ld_part, out, ld_out, 0, 1};
+  if (splits > 16 && total * 32 <= (int64_t)sm_count() * 2048 * 4) {
+    j.wide = 1;
+    j.blocks = (int32_t)min((int64_t)sm_count() * 8, (total * 32 + 255) / 256);
+  } else {
+    j.blocks = (int32_t)max((int64_t)1, min((int64_t)sm_count() * 4, (total + 255) / 256));
+  }
+  return j;
+}
+static inline void launch_split_reduce2(const ReduceJob& a, const ReduceJob& b, int32_t splits, cudaStream_t st) {
+  split_reduce2_kernel<<<(unsigned)(a.blocks + b.blocks), 256, 0, st>>>(a, b, splits);
+}
+
 // column sums of dz[M,N] (bias gradient), two fixed-order passes: per-CTA partials then a final sum
 __global__ void __launch_bounds__(256) colsum_partial_kernel(const float* __restrict__ dz, int64_t lddz, int64_t M,
                                                             int32_t N, int64_t rows_per_block,
@@ -618,12 +673,12 @@ HRB_API int hrb_dense_bwd_w_t(const float* xt, int64_t ldxt, const float* dzt, i
   // of the dz^T tiles anyway and leave one partial sum per (split, column)
   int rc = hrb_tc_gemm_splitk(xt, ldxt, dzt, lddzt, K, N, (int32_t)M, splits, part, ldp, dbias != nullptr ? colpart : nullptr, st);
   if (rc != HRB_OK) return rc;
-  launch_split_reduce(part, K, N, ldp, splits, dw, lddw, st);
-  HRB_LAUNCH_CHECK();
   if (dbias != nullptr) {
-    launch_split_reduce(colpart, 1, N, N, splits, dbias, N, st);
-    HRB_LAUNCH_CHECK();
+    launch_split_reduce2(reduce_job(part, K, N, ldp, splits, dw, lddw), reduce_job(colpart, 1, N, N, splits, dbias, N), splits, st);
+  } else {
+    launch_split_reduce(part, K, N, ldp, splits, dw, lddw, st);
   }
+  HRB_LAUNCH_CHECK();
   return HRB_OK;
 }
 
@@ -642,12 +697,12 @@ HRB_API int hrb_dense_bwd_w_xn(const float* x, int64_t ldx, const float* dzt, in
   float* colpart = part + (size_t)splits * K * ldp;
   int rc = hrb_tc_gemm_splitk_an(x, ldx, dzt, lddzt, K, N, (int32_t)M, splits, part, ldp, dbias != nullptr ? colpart : nullptr, st);
   if (rc != HRB_OK) return rc;
-  launch_split_reduce(part, K, N, ldp, splits, dw, lddw, st);
-  HRB_LAUNCH_CHECK();
   if (dbias != nullptr) {
-    launch_split_reduce(colpart, 1, N, N, splits, dbias, N, st);
-    HRB_LAUNCH_CHECK();
+    launch_split_reduce2(reduce_job(part, K, N, ldp, splits, dw, lddw), reduce_job(colpart, 1, N, N, splits, dbias, N), splits, st);
+  } else {
+    launch_split_reduce(part, K, N, ldp, splits, dw, lddw, st);
   }
+  HRB_LAUNCH_CHECK();
   return HRB_OK;
 }
 
@@ -690,12 +745,12 @@ HRB_API int hrb_dense1_bwd(const float* x, int64_t ldx, const float* w, const fl
     float* part = (float*)workspace;
     dense1_bwd_fused_kernel<<<grid, 256, fused_smem, st>>>(x, ldx, w, dy, M, K, act_prev, dz_prev, lddz, dz_prev_t, lddzt, part);
     HRB_LAUNCH_CHECK();
-    launch_split_reduce(part, 1, K, K + 1, grid, dw, K, st);
-    HRB_LAUNCH_CHECK();
     if (dbias != nullptr) {
-      launch_split_reduce(part + K, 1, 1, K + 1, grid, dbias, 1, st);
-      HRB_LAUNCH_CHECK();
+      launch_split_reduce2(reduce_job(part, 1, K, K + 1, grid, dw, K), reduce_job(part + K, 1, 1, K + 1, grid, dbias, 1), grid, st);
+    } else {
+      launch_split_reduce(part, 1, K, K + 1, grid, dw, K, st);
     }
+    HRB_LAUNCH_CHECK();
     return HRB_OK;
   }
   const int64_t total = M * (K / 4);
@@ -715,11 +770,11 @@ HRB_API int hrb_dense1_bwd(const float* x, int64_t ldx, const float* w, const fl
   dim3 grid((K + 31) / 32, yb);
   dense1_bwd_dw_kernel<<<grid, 256, 0, st>>>(x, ldx, dy, M, K, rpb, part);
   HRB_LAUNCH_CHECK();
-  launch_split_reduce(part, 1, K, K + 1, yb, dw, K, st);
-  HRB_LAUNCH_CHECK();
   if (dbias != nullptr) {
-    launch_split_reduce(part + K, 1, 1, K + 1, yb, dbias, 1, st);
-    HRB_LAUNCH_CHECK();
+    launch_split_reduce2(reduce_job(part, 1, K, K + 1, yb, dw, K), reduce_job(part + K, 1, 1, K + 1, yb, dbias, 1), yb, st);
+  } else {
+    launch_split_reduce(part, 1, K, K + 1, yb, dw, K, st);
   }
+  HRB_LAUNCH_CHECK();
   return HRB_OK;
 }

@@ -54,8 +54,7 @@ constexpr uint32_t UB_NONE = 0xFFFFFFFEu;
 constexpr int UB_SLICE_TARGET = 4096;        // positions per slice of a row the host knows to be hot
 constexpr int UB_PARTIAL_LD = 32 * 4 + 4;
 constexpr int UB_GATHER = 8;                 // warp batches whose gradient rows are in flight together
-constexpr int UB_APPLY = 2;
-constexpr int UB_DIRECT = 2;                 // singleton entries (gradient row + table row) a lane group has in flight together                  // row updates a lane group has in flight together
+constexpr int UB_APPLY = 2;                  // row updates a lane group has in flight together
 
 static inline size_t ub_align(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 

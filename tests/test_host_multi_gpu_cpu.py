@@ -1,5 +1,8 @@
-"""Checkpoint I/O host logic without a GPU: the file layout of single- and multi-GPU (row-sharded) models.
-The weights of a keras_lite model built on a machine without CUDA are CPU tensors; no kernel runs here."""
+"""Host logic of checkpoints and of the multi-GPU creation scope without a GPU: file layout of single- and multi-GPU (row-sharded)
+models, `ShardedTables`, `compile(distribute=...)`.  The weights of a keras_lite model built on a machine without
+CUDA are CPU tensors; no kernel runs here."""
+
+
 import json
 import os
 from types import SimpleNamespace
@@ -88,3 +91,39 @@ def test_sharded_table_refuses_the_layer_path():
     lay._sharded = (0, 2, 7000)
     with pytest.raises(RuntimeError, match="row-sharded"):
         lay.call(torch.zeros(4, 1, dtype=torch.int32))
+
+
+class _FakeComm:
+    def __init__(self, rank, n):
+        self.rank, self.N = rank, n
+
+
+def test_sharded_tables_scope_creates_row_shards_from_given_weights():
+    """Under `ShardedTables` a table above `min_rows` is CREATED as this rank's rows r % N == rank (here from pre-trained weights,
+    features/group.py:283-291, so that no kernel is needed); smaller tables stay whole."""
+    from handyrec_b200 import keras_lite as KL
+
+    big = np.arange(7000 * 8, dtype=np.float32).reshape(7000, 8)
+    small = np.arange(50 * 8, dtype=np.float32).reshape(50, 8)
+    for rank in range(3):
+        with KL.ShardedTables(_FakeComm(rank, 3), min_rows=1000):
+            pool = FeaturePool(pre_embd={"C0": small, "C1": big})
+            sparse = [SparseFeature("C0", 50, 8), SparseFeature("C1", 7000, 8)]
+            m = DeepFM(FeatureGroup("fm", sparse, pool, l2_embd=0.0), FeatureGroup("dnn", [DenseFeature("I0")] + sparse, pool, l2_embd=0.0),
+                       dnn_hidden_units=(8, 1))
+        assert KL.ShardedTables.active is None
+        lays = {l.input_dim: l for l in m._all_layers() if isinstance(l, CustomEmbedding)}
+        assert lays[50]._sharded is None and tuple(lays[50].embeddings.shape) == (50, 8)
+        assert lays[7000]._sharded == (rank, 3, 7000)
+        assert np.array_equal(lays[7000].embeddings.data.cpu().numpy(), big[rank::3])
+
+
+def test_distribute_refuses_graphs_the_engine_does_not_cover():
+    """A multi-GPU compile of a graph that does not lower onto the fused engine raises instead of training the layer path on a shard."""
+    from handyrec_b200 import keras_lite as KL
+
+    m = _model()
+    m.fuse = False  # stands for any graph `lowering.lower` declines (BatchNorm, Dropout, DIN, ...)
+    with pytest.raises(ValueError, match="multi-GPU"):
+        m.compile(optimizer=KL.Adam(1e-3), loss=KL.binary_crossentropy, distribute=_FakeComm(0, 2))
+    m.compile(optimizer=KL.Adam(1e-3), loss=KL.binary_crossentropy, distribute=_FakeComm(0, 1))  # one rank: nothing to shard

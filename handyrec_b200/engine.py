@@ -573,10 +573,6 @@ class DeepFMEngine:
             nB = upload(slot, nxt)
         while nxt is not None:
             cur_slot, B = slot, nB
-            nxt = next(it, None)
-            if nxt is not None:
-                slot ^= 1
-                nB = upload(slot, nxt)
             main.wait_event(self._stage_ready[cur_slot])
             ids_d, dense_d, label_d = self._stage[cur_slot]
             self.train_step_on_device(ids_d[:B], dense_d[:B] if self.n_dense else None, label_d[:B])
@@ -591,6 +587,12 @@ class DeepFMEngine:
             lh.copy_(self.loss_sum, non_blocking=True)  # D2H of this step's loss, not waited for here
             losses_host.append(lh)
             sizes.append(B)
+            # the next batch is fetched AFTER this step has been issued: the GPU never waits for the producer of batch t+1 before it
+            # may start batch t (the copy still overlaps step t: it only needs the other stage slot, free since step t-1)
+            nxt = next(it, None)
+            if nxt is not None:
+                slot ^= 1
+                nB = upload(slot, nxt)
         main.synchronize()
         return [float(l[0]) / b for l, b in zip(losses_host, sizes)]
 

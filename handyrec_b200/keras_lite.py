@@ -334,13 +334,19 @@ class Adam:
         from . import kernels as K
 
         self.t += 1
+        ps, gs, ms, vs, l2s = [], [], [], [], []
         for p, l2 in params_l2:
             if p.grad is None or not p.requires_grad:
                 continue
             if id(p) not in self.state:
                 self.state[id(p)] = (torch.zeros_like(p.data), torch.zeros_like(p.data))
             m, v = self.state[id(p)]
-            K.adam_step(p.data, p.grad.contiguous(), m, v, self.lr, self.b1, self.b2, self.eps, self.t, l2_scale=2.0 * l2)
+            ps.append(p.data)
+            gs.append(p.grad.contiguous())
+            ms.append(m)
+            vs.append(v)
+            l2s.append(2.0 * l2)
+        K.adam_step_multi(ps, gs, ms, vs, l2s, self.lr, self.b1, self.b2, self.eps, self.t)  # all variables in one launch
 
 
 class SGD:
@@ -350,9 +356,8 @@ class SGD:
     def step(self, params_l2):
         from . import kernels as K
 
-        for p, l2 in params_l2:
-            if p.grad is not None and p.requires_grad:
-                K.sgd_step(p.data, p.grad.contiguous(), self.lr, l2_scale=2.0 * l2)
+        live = [(p, l2) for p, l2 in params_l2 if p.grad is not None and p.requires_grad]
+        K.sgd_step_multi([p.data for p, _ in live], [p.grad.contiguous() for p, _ in live], [2.0 * l2 for _, l2 in live], self.lr)
 
 
 def binary_crossentropy(y_true, y_pred):

@@ -17,7 +17,7 @@ from ._lib import ACT, POOL, FieldDesc, OptParams, TableDesc, call
 __all__ = [
     "init_uniform", "embedding_fwd", "embedding_bwd_dense", "seq_pool_fwd", "seq_pool_bwd", "LookupPlan",
     "fm_fwd", "fm_bwd", "dense_fwd", "dense_bwd_x", "dense_bwd_w", "act_bwd", "dice_fwd", "dice_bwd",
-    "lau_fwd", "lau_pack_params", "sigmoid_bce", "adam_step", "sgd_step",
+    "lau_fwd", "lau_pack_params", "sigmoid_bce", "adam_step", "sgd_step", "adam_step_multi", "sgd_step_multi",
 ]
 
 
@@ -436,6 +436,32 @@ def adam_step(param, grad, m, v, lr, beta1=0.9, beta2=0.999, eps=1e-7, step=1, l
 
 def sgd_step(param, grad, lr, l2_scale=0.0):
     call("hrb_sgd_step", _p(param), _p(grad), param.numel(), lr, l2_scale, _stream())
+
+
+def _ptr_array(tensors):
+    return (ctypes.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
+
+
+def adam_step_multi(params, grads, ms, vs, l2_scales, lr, beta1=0.9, beta2=0.999, eps=1e-7, step=1):
+    """hrb_adam_step for a list of tensors in one launch (per HRB_MULTI_MAX tensors)."""
+    n = len(params)
+    if n == 0:
+        return
+    for t in list(params) + list(grads) + list(ms) + list(vs):
+        _chk(t, torch.float32, "tensor")
+    call("hrb_adam_step_multi", n, _ptr_array(params), _ptr_array(grads), _ptr_array(ms), _ptr_array(vs),
+         (ctypes.c_int64 * n)(*[p.numel() for p in params]), (ctypes.c_float * n)(*l2_scales), lr, beta1, beta2, eps,
+         1.0 - beta1 ** step, 1.0 - beta2 ** step, _stream())
+
+
+def sgd_step_multi(params, grads, l2_scales, lr):
+    n = len(params)
+    if n == 0:
+        return
+    for t in list(params) + list(grads):
+        _chk(t, torch.float32, "tensor")
+    call("hrb_sgd_step_multi", n, _ptr_array(params), _ptr_array(grads), (ctypes.c_int64 * n)(*[p.numel() for p in params]),
+         (ctypes.c_float * n)(*l2_scales), lr, _stream())
 
 
 # --------------------------------------------------------------------------------------------

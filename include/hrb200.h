@@ -364,6 +364,15 @@ int hrb_host_pack_set_writeback(int32_t on);
 int hrb_adam_step(float* param, const float* grad, float* m, float* v, int64_t n, float lr, float beta1,
                   float beta2, float eps, float bias_corr1, float bias_corr2, float l2_scale, void* stream);
 int hrb_sgd_step(float* param, const float* grad, int64_t n, float lr, float l2_scale, void* stream);
+/* The same steps for `count` parameter tensors in one launch per HRB_MULTI_MAX tensors (host arrays of device pointers / sizes /
+ * per-tensor l2 scales; l2_scale_host may be NULL).  The layer-by-layer models (DIN, the retrieval towers) hold 12-27 small
+ * tensors; Keras applies one optimiser op per variable (keras optimizer_v2 _resource_apply_dense), here they share a launch. */
+#define HRB_MULTI_MAX 32
+int hrb_adam_step_multi(int32_t count, float* const* param_host, const float* const* grad_host, float* const* m_host,
+                        float* const* v_host, const int64_t* n_host, const float* l2_scale_host, float lr, float beta1,
+                        float beta2, float eps, float bias_corr1, float bias_corr2, void* stream);
+int hrb_sgd_step_multi(int32_t count, float* const* param_host, const float* const* grad_host, const int64_t* n_host,
+                       const float* l2_scale_host, float lr, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * (e) row-sharded tables: owner(r) = r % n_ranks, local row r / n_ranks  (SURVEY §8e).

@@ -642,6 +642,35 @@ def test_sigmoid_bce_and_optimisers(dev):
     close(q, p0 - 0.1 * (g0 + 2e-3 * p0), FWD_TOL)
 
 
+def test_multi_tensor_optimizer_steps_match_the_single_tensor_ones(dev):
+    """hrb_adam_step_multi / hrb_sgd_step_multi: 37 tensors of odd sizes (two launches of <= 32) == one hrb_adam_step / hrb_sgd_step each."""
+    k = K()
+    sizes = [1, 3, 7, 128, 1000, 4097, 65536 + 5] + [11 * i + 1 for i in range(30)]
+    ps = [rnd(n, seed=100 + i) for i, n in enumerate(sizes)]
+    gs = [rnd(n, seed=300 + i) for i, n in enumerate(sizes)]
+    l2 = [0.0 if i % 3 else 2e-3 for i in range(len(sizes))]
+    a = [p.clone().to(dev) for p in ps]
+    am, av = [torch.zeros_like(t) for t in a], [torch.zeros_like(t) for t in a]
+    b = [p.clone().to(dev) for p in ps]
+    bm, bv = [torch.zeros_like(t) for t in b], [torch.zeros_like(t) for t in b]
+    gd = [g.to(dev) for g in gs]
+    for step in (1, 2):
+        k.adam_step_multi(a, gd, am, av, l2, 1e-2, step=step)
+        for i in range(len(sizes)):
+            k.adam_step(b[i], gd[i], bm[i], bv[i], lr=1e-2, step=step, l2_scale=l2[i])
+    for i in range(len(sizes)):  # same formulas; the two kernels may contract a*b+c differently, so equal to rounding, not bit for bit
+        close(a[i], b[i], 1e-6)
+        close(am[i], bm[i], 1e-6)
+        close(av[i], bv[i], 1e-6)
+    c = [p.clone().to(dev) for p in ps]
+    d = [p.clone().to(dev) for p in ps]
+    k.sgd_step_multi(c, gd, l2, 0.1)
+    for i in range(len(sizes)):
+        k.sgd_step(d[i], gd[i], lr=0.1, l2_scale=l2[i])
+        close(c[i], d[i], 1e-6)
+    k.adam_step_multi([], [], [], [], [], 1e-2)  # nothing to do
+
+
 # ------------------------------------------------------------------------------------------------
 # a11: BatchNormalization / Dropout inside DNN (layers/core.py:71-73)
 # ------------------------------------------------------------------------------------------------

@@ -539,3 +539,34 @@ def sharded_lookup_emulated(table: torch.Tensor, ids: torch.Tensor, n_ranks: int
     else:
         out = pmax.max(0).values
     return out.unsqueeze(1)
+
+
+# ---------------------------------------------------------------------------------------------
+# Scheduling invariant of the sorted embedding backward (handyrec_b200/csrc/lookup.cu, "long runs"): not reference arithmetic,
+# but a restatement of the classification every kernel of that path must agree on, so that the tests can check the claim the
+# kernels rely on -- the LOCAL test (four sample points around a position) equals the GLOBAL definition.
+# ---------------------------------------------------------------------------------------------
+def long_run_keys_global(sorted_keys: np.ndarray, step: int, sentinel: int) -> set:
+    """Rows whose run of equal keys covers two consecutive sample points (positions 0, step, 2*step, ... < n): what
+    bwd_long_detect_kernel lists."""
+    k = np.asarray(sorted_keys)
+    pts = np.arange(0, len(k), step)
+    return {int(k[pts[j]]) for j in range(len(pts) - 1) if k[pts[j]] == k[pts[j + 1]] and k[pts[j]] != sentinel}
+
+
+def long_run_local_test(sorted_keys: np.ndarray, step: int, sentinel: int, i: int) -> bool:
+    """run_is_long() of lookup.cu for the key at sorted position i: only the sample points around i are read."""
+    k = np.asarray(sorted_keys)
+    n, key = len(k), k[i]
+    if key == sentinel:
+        return False
+    p0 = i // step * step
+    s0 = k[p0]
+    s1 = k[p0 + step] if p0 + step < n else sentinel
+    if s0 == key and s1 == key:
+        return True
+    if s0 == key:
+        return p0 >= step and k[p0 - step] == key
+    if s1 == key:
+        return p0 + 2 * step < n and k[p0 + 2 * step] == key
+    return False

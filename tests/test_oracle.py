@@ -104,3 +104,34 @@ def test_log_uniform_sampler_distribution_and_uniqueness():
     assert sorted(ids.tolist()) == list(range(7))
     e = oracle.unique_expected_count(p, 30)
     assert np.all((e > 0) & (e <= 1)) and np.all(np.diff(e) < 0)
+
+
+def test_long_run_classification_is_a_local_property():
+    """The sorted backward takes "long" rows out of its chunk/merge chain.  The detect kernel lists a row when its run covers two
+    consecutive sample points; the chunk kernel decides per position from the four sample points around it.  Both must agree for
+    every position, whatever the run layout: skewed, runs ending exactly on sample points, sentinel tails, n not a multiple of the step."""
+    from oracle.layers_ref import long_run_keys_global, long_run_local_test
+
+    rng = np.random.RandomState(5)
+    step, sentinel = 8, 10 ** 6
+    for trial in range(300):
+        n = int(rng.randint(1, 200))
+        kind = trial % 4
+        if kind == 0:
+            keys = rng.randint(0, 6, n)
+        elif kind == 1:  # a few very long runs between singletons
+            keys = np.repeat(rng.randint(0, 50, 12), rng.randint(1, 40, 12))[:n]
+        elif kind == 2:  # run boundaries exactly on sample points
+            keys = np.repeat(np.arange(40), step * rng.randint(1, 4))[:n]
+        else:
+            keys = np.where(rng.rand(n) < 0.2, sentinel, rng.randint(0, 3, n))
+        keys = np.sort(keys)
+        long_rows = long_run_keys_global(keys, step, sentinel)
+        for i in range(len(keys)):
+            assert long_run_local_test(keys, step, sentinel, i) == (int(keys[i]) in long_rows), (trial, i, keys.tolist())
+        # every listed row is listed once by the detect rule "the first pair of the run reports it"
+        pts = np.arange(0, len(keys), step)
+        first_pairs = [int(keys[pts[j]]) for j in range(len(pts) - 1)
+                       if keys[pts[j]] == keys[pts[j + 1]] and keys[pts[j]] != sentinel and (j == 0 or keys[pts[j - 1]] != keys[pts[j]])]
+        assert sorted(first_pairs) == sorted(long_rows)
+        assert len(long_rows) <= len(keys) // (2 * step) + 2  # the bound the workspace is sized with

@@ -101,6 +101,17 @@ class CudaShardProvider:
         call("hrb_keyed_bwd_update", self.plan._h, K._p(keys), K._p(grads), n, ctypes.byref(op), K._p(self._ws_bwd), self._ws_bwd.numel(), K._stream())
 
 
+def exchange_offsets(count_matrix: Sequence[Sequence[int]], rank: int) -> Tuple[List[int], List[int], List[int]]:
+    """count_matrix[s][d] = entries rank s has for owner d  ->  (send_counts, recv_counts, dst_off) of `rank`:
+    dst_off[d] = first row `rank` writes in owner d's receive buffers = the entries of lower-ranked senders for d, so that every
+    owner's buffer ends up ordered by sender -- the layout of an all-to-all -- without the senders talking to each other."""
+    n = len(count_matrix)
+    send = [int(x) for x in count_matrix[rank]]
+    recv = [int(count_matrix[s][rank]) for s in range(n)]
+    off = [sum(int(count_matrix[s][d]) for s in range(rank)) for d in range(n)]
+    return send, recv, off
+
+
 class ReceiveBuffers:
     """This rank's receive blocks + the addresses of every rank's blocks as mapped here + the symmetric-memory handle (barriers)."""
 
@@ -230,10 +241,7 @@ class RowExchange:
             torch.cuda.current_stream().wait_event(self._route_done)
         if self.rx is not None:
             C = self._count_matrix_dev.tolist()  # the one host sync of the step
-            me = self.comm.rank
-            self.send_counts = [int(x) for x in C[me]]
-            self.recv_counts = [int(C[s][me]) for s in range(self.N)]
-            self.dst_off = [sum(int(C[s][d]) for s in range(me)) for d in range(self.N)]
+            self.send_counts, self.recv_counts, self.dst_off = exchange_offsets(C, self.comm.rank)
             self.n_send, self.n_recv = sum(self.send_counts), sum(self.recv_counts)
             if self.n_recv > self.rx.keys.shape[0]:
                 raise RuntimeError(f"gradient exchange: {self.n_recv} rows for this owner exceed the receive buffer ({self.rx.keys.shape[0]})")

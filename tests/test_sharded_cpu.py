@@ -69,3 +69,28 @@ def test_key_base_and_shard_rows():
     assert [shard_rows(3, r, 8) for r in range(8)] == [1, 1, 1, 1, 1, 1, 1, 1]  # empty shards still hold one (unused) row
     kb = key_base_table([10, 3], 4)
     assert kb[:, 0].tolist() == [0, 0, 0, 0] and kb[:, 1].tolist() == [3, 3, 2, 2]
+
+
+def test_exchange_offsets_reproduce_the_all_to_all_layout():
+    """The fused gather + exchange writes rank s's rows for owner d at exchange_offsets(...)[2][d] of d's receive buffer.  With every
+    rank doing that independently, each owner must hold exactly what an all-to-all ordered by sender would have delivered."""
+    import numpy as np
+
+    from handyrec_b200.sharded import exchange_offsets
+
+    rng = np.random.RandomState(0)
+    for n in (1, 2, 3, 8):
+        C = rng.randint(0, 50, (n, n)).tolist()
+        if n > 1:
+            C[1][0] = 0  # an empty segment
+        payload = {(s, d): [(s, d, i) for i in range(C[s][d])] for s in range(n) for d in range(n)}
+        buffers = [[None] * sum(C[s][d] for s in range(n)) for d in range(n)]
+        for s in range(n):
+            send, recv, off = exchange_offsets(C, s)
+            assert send == C[s] and recv == [C[r][s] for r in range(n)]
+            for d in range(n):
+                for i, item in enumerate(payload[(s, d)]):
+                    assert buffers[d][off[d] + i] is None  # no two senders write the same row
+                    buffers[d][off[d] + i] = item
+        for d in range(n):
+            assert buffers[d] == [item for s in range(n) for item in payload[(s, d)]]

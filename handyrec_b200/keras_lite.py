@@ -595,7 +595,15 @@ class Model:
                 history["loss"].append(tot / max(cnt, 1))
             # fused training leaves the dense / FM weights in the engine; they are handed back to the layers lazily, the first time
             # anything reads the layers (`layers`, `get_layer`, `predict` on the layer path, `save_weights`, `sync()`)
-            if validation_data is not None:
+            fused_val = (validation_data is not None and self._fused is not None and self._fused.engine is not None
+                         and isinstance(validation_data, tuple) and len(validation_data) == 2 and isinstance(validation_data[0], dict))
+            if fused_val:
+                # the fused engine's forward (the only reader a row-sharded table has); Keras' BCE on clipped probabilities
+                xv, yv = validation_data
+                p = np.clip(self._fused.predict(xv, batch_size).reshape(-1).astype(np.float64), 1e-7, 1.0 - 1e-7)
+                yt = np.asarray(yv, dtype=np.float64).reshape(-1)
+                history.setdefault("val_loss", []).append(float(-(yt * np.log(p) + (1.0 - yt) * np.log1p(-p)).mean()))
+            elif validation_data is not None:
                 vl, vc = 0.0, 0
                 with torch.no_grad():
                     for xb, yb in _batches(validation_data, None, batch_size)():

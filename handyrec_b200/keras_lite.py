@@ -478,6 +478,12 @@ class Model:
             self._fused.sync_to_layers()
 
     def predict(self, x, batch_size=None):
+        if (self._fused is not None and self._fused.engine is None and isinstance(x, dict) and self._comm is not None and self._comm.N > 1
+                and self.optimizer is not None):
+            # a multi-GPU model before its first fit: only the engine can read row-sharded tables, so it is built here (collective:
+            # every rank calls predict, as with fit)
+            n = len(np.asarray(next(iter(x.values()))))
+            self._fused.build(min(batch_size or n, n), self.optimizer)
         if self._fused is not None and self._fused.engine is not None and isinstance(x, dict):
             return self._fused.predict(x, batch_size)
         self.sync()

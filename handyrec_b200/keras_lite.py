@@ -37,7 +37,11 @@ class ShardedTables:
     r with r % N == rank (the counter-based initialiser gives every row the value it would have in the full table, so N ranks
     together hold exactly the table one GPU would have built from the same seed).  Such a table is read by the fused engine
     only (`compile` lowers the graph onto `ShardedDeepFMEngine`); a graph that does not lower raises instead of running the
-    layer path on a shard.  Smaller tables and dense weights are replicated and broadcast from rank 0 at compile time."""
+    layer path on a shard.  Smaller tables and dense weights are replicated and broadcast from rank 0 at compile time.
+
+    Collective calls: `fit` / `train_on_batch` / the first `predict` (they build or step the engine) must be made by every rank, with
+    the same `batch_size` and the same number of batches -- like any data-parallel training loop.  `predict` after the first `fit`
+    and `save_weights` / `load_weights` are rank-local."""
 
     active: Optional["ShardedTables"] = None
 

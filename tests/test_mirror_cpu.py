@@ -151,3 +151,68 @@ def test_models_construct_and_raise():
     assert m2.outputs.shape == (None, 1) and "hist_movie" in [i.name for i in m2.inputs]
     # H7: item_seq group comes first with mask_zero=True; the other group reuses that masked table
     assert g2["other_feature_group"].embd_layers["movie_id"] is g2["item_seq_feat_group"].embd_layers["movie_id"]
+
+
+# ------------------------------------------------------------------------------------------------
+# lowering: which graphs the fused engine takes (handyrec_b200/lowering.py) -- pattern matching only, no kernel runs
+# ------------------------------------------------------------------------------------------------
+def _deepfm(fm_feats, dnn_feats, pool=None, **kw):
+    from handyrec_b200.models import DeepFM
+
+    pool = pool or FeaturePool()
+    return DeepFM(FeatureGroup("fm", fm_feats, pool, l2_embd=0.0), FeatureGroup("dnn", dnn_feats, pool, l2_embd=0.0), **kw)
+
+
+def test_lowering_accepts_the_deepfm_graphs_the_engine_covers():
+    from handyrec_b200.lowering import match_deepfm
+
+    sparse = [SparseFeature("a", 50, 8), SparseFeature("b", 7, 8)]
+    hist = SparseSeqFeature(SparseFeature("item", 30, 8), "hist", 5)
+    dense = [DenseFeature("d0"), DenseFeature("d1")]
+    spec = match_deepfm(_deepfm(sparse + [hist], dense + sparse + [hist], dnn_hidden_units=(16, 8, 1)))
+    assert spec is not None
+    assert [(f.inp.name, f.seq_len, f.pool) for f in spec.fields] == [("a", 1, "none"), ("b", 1, "none"), ("hist", 5, "mean")]
+    assert [t.name for t in spec.dense_inputs] == ["d0", "d1"] and tuple(spec.dnn.hidden_units) == (16, 8, 1)
+    # no dense features at all; sigmoid / tanh towers
+    assert match_deepfm(_deepfm(sparse, sparse, dnn_hidden_units=(8, 1), dnn_activation="tanh")) is not None
+    # a table shared by a plain and a sequence feature is ONE engine table with two fields
+    item = SparseFeature("item", 30, 8)
+    shared = match_deepfm(_deepfm([item, SparseSeqFeature(item, "hist", 4)], [item, SparseSeqFeature(item, "hist", 4)], dnn_hidden_units=(8, 1)))
+    assert shared is not None and shared.fields[0].emb is shared.fields[1].emb
+
+
+@pytest.mark.parametrize("case", ["bn", "dropout", "dice", "different_groups", "mixed_dims", "dim_not_multiple_of_4"])
+def test_lowering_declines_what_the_engine_does_not_cover(case):
+    """Declined graphs keep the layer-by-layer path (same results, more launches): BatchNorm / Dropout in the tower, Dice, FM and DNN
+    groups over different features (the engine shares ONE lookup), more than one embedding dim, a dim the 16-byte row chunks do not divide."""
+    from handyrec_b200.lowering import match_deepfm
+
+    a, b, c = SparseFeature("a", 50, 8), SparseFeature("b", 7, 8), SparseFeature("c", 9, 8)
+    if case == "bn":
+        m = _deepfm([a, b], [a, b], dnn_hidden_units=(8, 1), dnn_bn=True)
+    elif case == "dropout":
+        m = _deepfm([a, b], [a, b], dnn_hidden_units=(8, 1), dnn_dropout=0.3)
+    elif case == "dice":
+        m = _deepfm([a, b], [a, b], dnn_hidden_units=(8, 1), dnn_activation="dice")
+    elif case == "different_groups":
+        m = _deepfm([a, b], [a, b, c], dnn_hidden_units=(8, 1))
+    elif case == "mixed_dims":
+        try:
+            m = _deepfm([a, SparseFeature("w", 5, 16)], [a, SparseFeature("w", 5, 16)], dnn_hidden_units=(8, 1))
+        except Exception:  # the FM layer itself needs one embedding dim (interaction.py:26-39): nothing to lower
+            m = None
+    else:
+        m = _deepfm([SparseFeature("p", 5, 6), SparseFeature("q", 5, 6)], [SparseFeature("p", 5, 6), SparseFeature("q", 5, 6)], dnn_hidden_units=(8, 1))
+    if m is None:
+        return  # such a DeepFM cannot even be built
+    assert match_deepfm(m) is None
+
+
+def test_lowering_declines_other_model_families():
+    from handyrec_b200.config import ConfigLoader
+    from handyrec_b200.lowering import match_deepfm
+    from handyrec_b200.models import DIN
+
+    g = ConfigLoader(DIN_CFG).prepare_features(FEATURE_DIM)
+    m = DIN(g["item_seq_feat_group"], g["other_feature_group"], dnn_hidden_units=(8,), lau_dnn_hidden_units=(8, 1))
+    assert match_deepfm(m) is None

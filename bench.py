@@ -257,7 +257,9 @@ def main():
     peaks = load_peaks()
     # ONE nvidia-smi process (rank 0) samples every GPU of the job; it is started here, seconds before the timed region, so that its
     # start-up (NVML walks all GPUs) is over when the timing begins -- samples count from ClockSampler.mark() on
-    clocks = ClockSampler(list(range(world))) if rank == 0 else None
+    vis = [v.strip() for v in os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",") if v.strip()]
+    gpu_ids = vis[:world] if len(vis) >= world else list(range(world))  # nvidia-smi counts physical GPUs: follow CUDA_VISIBLE_DEVICES if it is set
+    clocks = ClockSampler(gpu_ids) if rank == 0 else None
     if clocks is not None:
         clocks.start()
 

@@ -176,7 +176,8 @@ def run(args, load_peaks, ClockSampler, WORKLOADS, METRICS):
     torch.cuda.set_device(0)
     dev = torch.device("cuda", 0)
     peaks = load_peaks()
-    clocks = ClockSampler(0)  # started before the model is built: its start-up is over when the timing begins; samples count from mark()
+    vis = [v.strip() for v in os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",") if v.strip()]
+    clocks = ClockSampler(vis[0] if vis else 0)  # started before the model is built: its start-up is over when the timing begins; samples count from mark()
     clocks.start()
     wl = args.workload
     if wl == "din":
